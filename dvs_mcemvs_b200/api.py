@@ -1,0 +1,419 @@
+"""Python mirror of the reference's mapping-path classes over the C-ABI.
+
+Names and argument meaning follow the reference so that tests read like the reference's
+callers (paths relative to the reference root):
+
+    ShapeDSI, MapperEMVS      mapper_emvs_stereo/include/mapper_emvs_stereo/mapper_emvs_stereo.hpp:40-155
+    Grid3D                    cartesian3dgrid/include/cartesian3dgrid/cartesian3dgrid.h:22-247
+    LinearTrajectory          mapper_emvs_stereo/include/mapper_emvs_stereo/trajectory.hpp:80-127
+    process_1                 mapper_emvs_stereo/src/process1.cpp:28-224 (steps 1-3, no file output)
+
+All compute happens in libemvs_b200.so (hand-written sm_100a CUDA).  There is no CPU path:
+constructing a Context without a B200-class GPU raises EmvsError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import (EVENT_DTYPE, PACKET_DTYPE, POSE_DTYPE, STAMPED_POSE_DTYPE, Camera, EmvsError, Shape, check, ptr)
+
+
+def _lib():
+    return capi.load()
+
+
+# --------------------------------------------------------------------------------------------
+# plain data
+# --------------------------------------------------------------------------------------------
+class ShapeDSI:
+    """EMVS::ShapeDSI(dimX, dimY, dimZ, min_depth, max_depth, fov) — mapper_emvs_stereo.hpp:40-65.
+
+    ``inverse_depth`` selects the compile-time USE_INVERSE_DEPTH variant (CMakeLists.txt:41-44)."""
+
+    def __init__(self, dimX, dimY, dimZ, min_depth, max_depth, fov, inverse_depth=False):
+        self.dimX_, self.dimY_, self.dimZ_ = int(dimX), int(dimY), int(dimZ)
+        self.min_depth_, self.max_depth_, self.fov_ = float(min_depth), float(max_depth), float(fov)
+        self.inverse_depth = bool(inverse_depth)
+
+    def c_struct(self):
+        return Shape(self.dimX_, self.dimY_, self.dimZ_, self.min_depth_, self.max_depth_, self.fov_,
+                     1 if self.inverse_depth else 0)
+
+
+class CameraModel:
+    """The part of image_geometry::PinholeCameraModel the mapper reads (mapper_emvs_stereo.cpp:34-48):
+    fullResolution() and fx(), fy(), cx(), cy() of the projection matrix, plus the rectification
+    LUT that precomputeRectifiedPoints (:256-299) derives from it with OpenCV — here an input."""
+
+    def __init__(self, width, height, fx, fy, cx, cy, lut=None):
+        self.width, self.height = int(width), int(height)
+        self.fx, self.fy, self.cx, self.cy = float(fx), float(fy), float(cx), float(cy)
+        if lut is None:  # zero distortion: rectified pixel == raw pixel
+            xs, ys = np.meshgrid(np.arange(self.width, dtype=np.float32), np.arange(self.height, dtype=np.float32))
+            lut = np.stack([xs, ys], axis=-1)
+        self.lut = np.ascontiguousarray(lut, dtype=np.float32).reshape(self.height * self.width, 2)
+
+    def c_struct(self):
+        return Camera(self.width, self.height, self.fx, self.fy, self.cx, self.cy)
+
+
+def make_pose(q=(1.0, 0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0)):
+    p = np.zeros((), dtype=POSE_DTYPE)
+    p["q"] = q
+    p["t"] = t
+    return p
+
+
+def pose_compose(a, b):
+    out = np.zeros((), dtype=POSE_DTYPE)
+    check(_lib().emvs_pose_compose(ptr(np.ascontiguousarray(a)), ptr(np.ascontiguousarray(b)), ptr(out)))
+    return out
+
+
+def pose_inverse(a):
+    out = np.zeros((), dtype=POSE_DTYPE)
+    check(_lib().emvs_pose_inverse(ptr(np.ascontiguousarray(a)), ptr(out)))
+    return out
+
+
+class LinearTrajectory:
+    """LinearTrajectory(poses) — trajectory.hpp:80-127.  ``poses``: array of STAMPED_POSE_DTYPE
+    sorted by strictly increasing time (the std::map ordering)."""
+
+    def __init__(self, poses):
+        poses = np.ascontiguousarray(poses, dtype=STAMPED_POSE_DTYPE)
+        if poses.shape[0] < 2:
+            raise ValueError("At least two poses need to be provided")  # trajectory.hpp:89
+        self.poses = poses
+
+    def getPoseAt(self, sec, nsec):
+        """Returns the pose or None when t is outside the control poses (getPoseAt -> false)."""
+        out = np.zeros((), dtype=POSE_DTYPE)
+        found = C.c_int(0)
+        check(_lib().emvs_trajectory_pose_at(ptr(self.poses), self.poses.shape[0], int(sec), int(nsec), ptr(out),
+                                             C.byref(found)))
+        return out if found.value else None
+
+    def getNumControlPoses(self):
+        return self.poses.shape[0]
+
+
+# --------------------------------------------------------------------------------------------
+# device objects
+# --------------------------------------------------------------------------------------------
+class Context:
+    """One CUDA device + stream + scratch (emvs_context)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(_lib().emvs_context_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().emvs_context_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def sync(self):
+        check(_lib().emvs_context_sync(self._h))
+
+    def set_slab(self, planes):
+        check(_lib().emvs_context_set_slab(self._h, int(planes)))
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        check(_lib().emvs_context_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def timer(self):
+        return Timer(self)
+
+    def profile_vote(self, enable=True):
+        check(_lib().emvs_context_profile_vote(self._h, 1 if enable else 0))
+
+    def vote_time(self):
+        """-> (summed device ms of the vote-kernel launches since profile_vote(True), launch count)"""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        check(_lib().emvs_context_vote_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # multi-GPU
+    def comm_init(self, unique_id, n_ranks, rank):
+        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        check(_lib().emvs_comm_init(self._h, ptr(buf), int(n_ranks), int(rank)))
+
+    def comm_destroy(self):
+        check(_lib().emvs_comm_destroy(self._h))
+
+
+def comm_unique_id():
+    buf = np.zeros(128, dtype=np.uint8)
+    check(_lib().emvs_comm_unique_id(ptr(buf)))
+    return buf.tobytes()
+
+
+class Timer:
+    def __init__(self, ctx):
+        h = C.c_void_p()
+        check(_lib().emvs_timer_create(ctx._h, C.byref(h)))
+        self._h = h
+
+    def start(self):
+        check(_lib().emvs_timer_start(self._h))
+
+    def stop(self):
+        check(_lib().emvs_timer_stop(self._h))
+
+    def elapsed_ms(self):
+        ms = C.c_float(0)
+        check(_lib().emvs_timer_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib().emvs_timer_destroy(self._h)
+            self._h = None
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by pinned host memory (cudaHostAlloc); keep the returned array alive."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(_lib().emvs_host_alloc(n, C.byref(p)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    return arr
+
+
+_PINNED = {}
+
+
+class Grid3D:
+    """Grid3D(dimX, dimY, dimZ) — cartesian3dgrid.h:22-247; the volume lives in HBM."""
+
+    def __init__(self, ctx, dimX, dimY, dimZ, _handle=None, _owner=None):
+        self.ctx = ctx
+        self._owner = _owner  # a MapperEMVS keeps its dsi_ alive
+        if _handle is None:
+            h = C.c_void_p()
+            check(_lib().emvs_grid_create(ctx._h, int(dimX), int(dimY), int(dimZ), C.byref(h)))
+            self._h, self._owned = h, True
+        else:
+            self._h, self._owned = _handle, False
+        self.size_ = (int(dimX), int(dimY), int(dimZ))
+
+    def close(self):
+        if getattr(self, "_owned", False) and self._h:
+            _lib().emvs_grid_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def getDimensions(self):
+        return self.size_
+
+    def resetGrid(self):
+        check(_lib().emvs_grid_reset(self._h))
+
+    def _op(self, other, op, n=0, eps=0.0):
+        check(_lib().emvs_grid_op(self._h, other._h if other is not None else None, op, int(n), float(eps)))
+
+    # cartesian3dgrid.h:64-192 — same names, same defaults
+    def addTwoGrids(self, g): self._op(g, capi.OP_ADD)
+    def addInverseOfTwoGrids(self, g, eps=1e-2): self._op(g, capi.OP_ADD_INV, 0, eps)
+    def computeHMfromSumOfInv(self, n): self._op(None, capi.OP_HM_FROM_SUMINV, n)
+    def computeAMfromSum(self, n): self._op(None, capi.OP_AM_FROM_SUM, n)
+    def minTwoGrids(self, g): self._op(g, capi.OP_MIN)
+    def geometricMeanTwoGrids(self, g): self._op(g, capi.OP_GM)
+    def arithmeticMeanTwoGrids(self, g): self._op(g, capi.OP_AM)
+    def rmsTwoGrids(self, g): self._op(g, capi.OP_RMS)
+    def maxTwoGrids(self, g): self._op(g, capi.OP_MAX)
+
+    def harmonicMeanTwoGrids(self, g, n=None, eps=1e-1):
+        if n is None:
+            self._op(g, capi.OP_HM, 2, eps)
+        else:
+            self._op(g, capi.OP_HM_N, n, eps)
+
+    def copyFrom(self, g):
+        """resetGrid(); addTwoGrids(g) — the initialisation idiom of process1.cpp:126-127."""
+        check(_lib().emvs_grid_copy(self._h, g._h))
+
+    def computeMeanSquare(self):
+        out = C.c_double(0)
+        check(_lib().emvs_grid_mean_square(self._h, C.byref(out)))
+        return out.value
+
+    def collapseMaxZSlice(self, depths=None):
+        """-> (max_val float32 [dimY, dimX], max_pos_idx uint8|uint16 [dimY, dimX][, depth])."""
+        dimX, dimY, dimZ = self.size_
+        conf = np.empty((dimY, dimX), np.float32)
+        idx = np.empty((dimY, dimX), np.uint8 if dimZ <= 256 else np.uint16)
+        depth = np.empty((dimY, dimX), np.float32) if depths is not None else None
+        d = np.ascontiguousarray(depths, np.float32) if depths is not None else None
+        check(_lib().emvs_grid_collapse_max(self._h, ptr(d), ptr(conf), ptr(idx), ptr(depth)))
+        return (conf, idx) if depth is None else (conf, idx, depth)
+
+    def download(self):
+        """Host copy, shape [dimZ, dimY, dimX] (the layout writeGridNpy dumps, cartesian3dgrid_IO.cpp:30-36)."""
+        dimX, dimY, dimZ = self.size_
+        out = np.empty((dimZ, dimY, dimX), np.float32)
+        check(_lib().emvs_grid_download(self._h, ptr(out)))
+        return out
+
+    def upload(self, vol):
+        dimX, dimY, dimZ = self.size_
+        vol = np.ascontiguousarray(vol, np.float32)
+        assert vol.size == dimX * dimY * dimZ
+        check(_lib().emvs_grid_upload(self._h, ptr(vol)))
+
+    def device_ptr(self):
+        p = C.c_void_p()
+        check(_lib().emvs_grid_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def allreduce(self):
+        check(_lib().emvs_grid_allreduce(self._h))
+
+    def allreduce_async(self):
+        check(_lib().emvs_grid_allreduce_async(self._h))
+
+
+def fuse_collapse(grids, method, depths=None, fused_out=None):
+    """Fast path of process_1 steps 2+3: n-ary fusion + Z-argmax without materialising the fused DSI."""
+    g0 = grids[0]
+    dimX, dimY, dimZ = g0.size_
+    arr = (C.c_void_p * len(grids))(*[g._h for g in grids])
+    conf = np.empty((dimY, dimX), np.float32)
+    idx = np.empty((dimY, dimX), np.uint8 if dimZ <= 256 else np.uint16)
+    depth = np.empty((dimY, dimX), np.float32) if depths is not None else None
+    d = np.ascontiguousarray(depths, np.float32) if depths is not None else None
+    check(_lib().emvs_fuse_collapse(arr, len(grids), int(method), ptr(d), fused_out._h if fused_out else None,
+                                    ptr(conf), ptr(idx), ptr(depth)))
+    return (conf, idx) if depth is None else (conf, idx, depth)
+
+
+def fuse_collapse_device(grids, method, d_depths, d_conf, d_idx, d_depth, fused_out=None):
+    """fuse_collapse with DEVICE pointers (ints) for the depth table and the outputs; asynchronous on
+    the context's stream, nothing travels to the host."""
+    arr = (C.c_void_p * len(grids))(*[g._h for g in grids])
+    check(_lib().emvs_fuse_collapse_device(arr, len(grids), int(method), C.c_void_p(d_depths),
+                                           fused_out._h if fused_out else None, C.c_void_p(d_conf),
+                                           C.c_void_p(d_idx), C.c_void_p(d_depth) if d_depth else None))
+
+
+class MapperEMVS:
+    """EMVS::MapperEMVS(cam, dsi_shape) — mapper_emvs_stereo.hpp:94-155."""
+
+    def __init__(self, ctx, cam, dsi_shape):
+        self.ctx, self.cam, self.name = ctx, cam, ""
+        h = C.c_void_p()
+        cs, ss = cam.c_struct(), dsi_shape.c_struct()
+        check(_lib().emvs_mapper_create(ctx._h, C.byref(cs), C.byref(ss), C.byref(h)))
+        self._h = h
+        shape = Shape()
+        virt = np.zeros(4, np.float32)
+        check(_lib().emvs_mapper_shape(self._h, C.byref(shape), ptr(virt)))
+        self.dsi_shape_ = ShapeDSI(shape.dimX, shape.dimY, shape.dimZ, shape.min_depth, shape.max_depth,
+                                   shape.fov_deg, bool(shape.inverse_depth))
+        self.virtual_cam_ = virt  # fx, fy, cx, cy
+        self.raw_depths_vec_ = np.zeros(shape.dimZ, np.float32)
+        check(_lib().emvs_mapper_depths(self._h, ptr(self.raw_depths_vec_)))
+        check(_lib().emvs_mapper_set_lut(self._h, ptr(cam.lut), cam.lut.shape[0]))
+        gh = C.c_void_p()
+        check(_lib().emvs_mapper_grid(self._h, C.byref(gh)))
+        self.dsi_ = Grid3D(ctx, shape.dimX, shape.dimY, shape.dimZ, _handle=gh, _owner=self)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().emvs_mapper_destroy(self._h)
+            self._h = None
+            self.dsi_._h = None
+
+    __del__ = close
+
+    def packetize(self, events, trajectory, T_rv_w):
+        """Packet stage of evaluateDSI (mapper_emvs_stereo.cpp:86-126) -> packets, or None if < 1024 events."""
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        n = events.shape[0]
+        out = np.zeros(n // capi.PACKET_SIZE + 1, dtype=PACKET_DTYPE)
+        n_pk = C.c_size_t(0)
+        cs = self.cam.c_struct()
+        rc = _lib().emvs_packetize(ptr(events), n, ptr(trajectory.poses), trajectory.poses.shape[0],
+                                   ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE)), C.byref(cs),
+                                   ptr(self.virtual_cam_), float(self.raw_depths_vec_[0]), ptr(out), out.shape[0],
+                                   C.byref(n_pk))
+        if rc == capi.EMVS_ERR_TOO_FEW:
+            return None
+        check(rc)
+        return out[:n_pk.value]
+
+    def evaluateDSI(self, events, trajectory, T_rv_w):
+        """bool evaluateDSI(events, trajectory, T_rv_w) — mapper_emvs_stereo.cpp:67-148."""
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        rc = _lib().emvs_mapper_evaluate_dsi(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
+                                             trajectory.poses.shape[0],
+                                             ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE)))
+        if rc == capi.EMVS_ERR_TOO_FEW:
+            return False
+        check(rc)
+        return True
+
+    def build(self, events, packets, accumulate=False):
+        """Event stage + reset + fillVoxelGrid (mapper_emvs_stereo.cpp:129-205) for given packets."""
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        packets = np.ascontiguousarray(packets, dtype=PACKET_DTYPE)
+        check(_lib().emvs_mapper_build(self._h, ptr(events), events.shape[0], ptr(packets), packets.shape[0],
+                                       capi.BUILD_ACCUMULATE if accumulate else capi.BUILD_RESET))
+
+    def build_device(self, d_events, n_events, d_packets, n_packets, accumulate=False):
+        """Same with device pointers (ints); asynchronous on the context's stream."""
+        check(_lib().emvs_mapper_build_device(self._h, C.c_void_p(d_events), int(n_events), C.c_void_p(d_packets),
+                                              int(n_packets),
+                                              capi.BUILD_ACCUMULATE if accumulate else capi.BUILD_RESET))
+
+    def depths_device_ptr(self):
+        p = C.c_void_p()
+        check(_lib().emvs_mapper_depths_device(self._h, C.byref(p)))
+        return p.value
+
+    def counts(self):
+        out = np.zeros(self.dsi_shape_.dimZ_, np.uint64)
+        check(_lib().emvs_mapper_counts(self._h, ptr(out)))
+        return out
+
+    def counts_allreduce(self):
+        check(_lib().emvs_mapper_counts_allreduce(self._h))
+
+    def getDepthMapFromDSI(self):
+        """Hot part of getDepthMapFromDSI (mapper_emvs_stereo.cpp:344-375 + :302-313, method=-1):
+        -> (depth_map, confidence_map, depth_cell_indices) with depth = depths[raw argmax]."""
+        conf, idx, depth = self.dsi_.collapseMaxZSlice(self.raw_depths_vec_)
+        return depth, conf, idx
+
+
+# --------------------------------------------------------------------------------------------
+# process_1 (Alg. 1: fusion across cameras) — process1.cpp:28-224, compute steps only
+# --------------------------------------------------------------------------------------------
+def process_1(mappers, events, trajectories, T_rv_w, fusion_method, mapper_fused=None):
+    """Back-project every camera's events, fuse the DSIs, extract depth + confidence.
+
+    mappers/events/trajectories: one entry per camera (2 or 3 in the reference; more is an
+    extension).  Returns (depth_map, confidence_map, depth_cell_indices).  If ``mapper_fused`` is
+    given its dsi_ receives the fused volume (the reference always materialises it)."""
+    if fusion_method not in (1, 2, 3, 4, 5, 6):
+        raise ValueError("Improper fusion method selected")  # process1.cpp:155-157
+    for m, ev, tr in zip(mappers, events, trajectories):
+        m.evaluateDSI(ev, tr, T_rv_w)
+    grids = [m.dsi_ for m in mappers]
+    if fusion_method in (3, 4, 5) and len(grids) == 3:
+        grids = grids[:2]  # reference quirk: the third camera is ignored for GM/AM/RMS (process1.cpp:178-183)
+    conf, idx, depth = fuse_collapse(grids, fusion_method, mappers[0].raw_depths_vec_,
+                                     mapper_fused.dsi_ if mapper_fused is not None else None)
+    return depth, conf, idx

@@ -1,0 +1,999 @@
+// emvs_engine.cu — context / grid / mapper objects and the C-ABI of include/emvs_b200.h.
+// Host orchestration only; device code lives in emvs_kernels.cuh.  No CPU fallback: every
+// compute entry point launches CUDA kernels or fails.
+
+#include "emvs_internal.h"
+#include "emvs_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace emvs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace emvs
+
+using namespace emvs;
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, #expr); \
+      return EMVS_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+#define REQUIRE(cond, code, msg)  \
+  do {                            \
+    if (!(cond)) {                \
+      set_error("%s", msg);       \
+      return code;                \
+    }                             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct emvs_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  uint32_t slab_override = 0;
+  // quad scratch for one slab of planes; invariant: all zero between builds
+  float4* quad = nullptr;
+  size_t quad_bytes = 0;
+  // grow-only device staging
+  void* d_events = nullptr;  size_t events_cap = 0;
+  void* d_packets = nullptr; size_t packets_cap = 0;
+  float2* d_xy0 = nullptr;   size_t xy0_cap = 0;
+  void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
+  double* d_partial = nullptr;                        // 1024 partial sums + 1 result
+  // pinned host staging for packets produced by evaluate_dsi
+  emvs_packet* h_packets = nullptr; size_t h_packets_cap = 0;
+  // NCCL
+  void* comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  // optional per-launch timing of the vote kernel (bench roofline): event pairs on `stream`
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), prof_used of them recorded
+  size_t prof_used = 0;
+};
+
+struct emvs_grid {
+  emvs_context* ctx = nullptr;
+  uint32_t dimX = 0, dimY = 0, dimZ = 0;
+  size_t n_cells = 0;
+  float* d = nullptr;
+};
+
+struct emvs_mapper {
+  emvs_context* ctx = nullptr;
+  emvs_camera cam{};
+  emvs_shape shape{};   // resolved (dimX/dimY filled in)
+  float virt[4] = {0, 0, 0, 0};
+  std::vector<float> depths;
+  float* d_depths = nullptr;
+  float2* d_lut = nullptr;
+  bool lut_set = false;
+  emvs_grid* grid = nullptr;
+  unsigned long long* d_counts = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int grow(void** p, size_t* cap, size_t need)
+{
+  if (need <= *cap) return EMVS_OK;
+  if (*p) CUDA_TRY(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  CUDA_TRY(cudaMalloc(p, need));
+  *cap = need;
+  return EMVS_OK;
+}
+
+inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// Planes voted per pass over the event list.  The quad scratch of a slab (4 copies) must stay
+// L2-resident together with the streaming event reads; 32 MiB is a conservative default for
+// the 126 MB L2 (tuned with tools/red_microbench).
+uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ)
+{
+  uint32_t s = ctx->slab_override;
+  if (!s) {
+    if (const char* env = getenv("EMVS_SLAB")) s = (uint32_t)atoi(env);
+  }
+  if (!s) {
+    const size_t plane_bytes = (size_t)ceil_div(dimX, 2) * ceil_div(dimY, 2) * 64;
+    const size_t budget = (size_t)32 << 20;
+    s = (uint32_t)std::max<size_t>(1, budget / std::max<size_t>(plane_bytes, 1));
+  }
+  s = std::min(s, dimZ);
+  s = std::min<uint32_t>(s, 1024);
+  return std::max<uint32_t>(s, 1);
+}
+
+int ensure_quad(emvs_context* ctx, size_t bytes)
+{
+  if (bytes <= ctx->quad_bytes) return EMVS_OK;
+  if (ctx->quad) CUDA_TRY(cudaFree(ctx->quad));
+  ctx->quad = nullptr;
+  ctx->quad_bytes = 0;
+  CUDA_TRY(cudaMalloc((void**)&ctx->quad, bytes));
+  ctx->quad_bytes = bytes;
+  CUDA_TRY(cudaMemsetAsync(ctx->quad, 0, bytes, ctx->stream));
+  return EMVS_OK;
+}
+
+// Device part of evaluateDSI: event stage, (reset), slab loop of {vote, merge, re-zero}.
+int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, const emvs_packet* d_pk,
+                    size_t n_packets, int flags)
+{
+  emvs_context* ctx = m->ctx;
+  emvs_grid* g = m->grid;
+  const bool accumulate = (flags & EMVS_BUILD_ACCUMULATE) != 0;
+  cudaStream_t st = ctx->stream;
+  if (!accumulate) {
+    CUDA_TRY(cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned long long) * g->dimZ, st));
+  }
+  if (n_packets == 0) {
+    if (!accumulate) CUDA_TRY(cudaMemsetAsync(g->d, 0, g->n_cells * sizeof(float), st));
+    return EMVS_OK;
+  }
+  (void)n_events;
+  const size_t n_voted = n_packets * (size_t)EMVS_PACKET_SIZE;
+  {
+    const int rc = grow((void**)&ctx->d_xy0, &ctx->xy0_cap, n_voted * sizeof(float2));
+    if (rc) return rc;
+  }
+  const uint32_t dimX = g->dimX, dimY = g->dimY, dimZ = g->dimZ;
+  const uint32_t QW = ceil_div(dimX, 2), QH = ceil_div(dimY, 2);
+  const uint32_t slab = choose_slab(ctx, dimX, dimY, dimZ);
+  const size_t slab_bytes = (size_t)slab * QW * QH * 4 * sizeof(float4);
+  {
+    const int rc = ensure_quad(ctx, slab_bytes);
+    if (rc) return rc;
+  }
+
+  {
+    const unsigned blocks = (unsigned)((n_voted + 255) / 256);
+    k_warp_events<<<blocks, 256, 0, st>>>(d_ev, d_pk, m->d_lut, m->cam.width, m->cam.height, ctx->d_xy0,
+                                          (unsigned long long)n_voted);
+    ctx->launches++;
+  }
+
+  VoteParams P;
+  P.vfx = m->virt[0]; P.vfy = m->virt[1]; P.vcx = m->virt[2]; P.vcy = m->virt[3];
+  P.z0 = m->depths[0];
+  P.xmax = (float)((int)dimX - 1);
+  P.ymax = (float)((int)dimY - 1);
+  P.QW = QW; P.QH = QH;
+
+  for (uint32_t k0 = 0; k0 < dimZ; k0 += slab) {
+    const uint32_t nk = std::min(slab, dimZ - k0);
+    const size_t smem = nk * (sizeof(float4) + sizeof(unsigned int));
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (ctx->profile) {
+      if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreate(&a));
+        CUDA_TRY(cudaEventCreate(&b));
+        ctx->prof_events.push_back(a);
+        ctx->prof_events.push_back(b);
+      }
+      pe0 = ctx->prof_events[ctx->prof_used];
+      pe1 = ctx->prof_events[ctx->prof_used + 1];
+      ctx->prof_used += 2;
+      CUDA_TRY(cudaEventRecord(pe0, st));
+    }
+    k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad,
+                                                            m->d_counts);
+    ctx->launches++;
+    if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
+    dim3 mb(32, 8, 1), mg(ceil_div(QW, 32), ceil_div(QH, 8), nk);
+    k_merge_quads<<<mg, mb, 0, st>>>(ctx->quad, g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
+                                     accumulate ? 1 : 0);
+    ctx->launches++;
+    CUDA_TRY(cudaMemsetAsync(ctx->quad, 0, (size_t)nk * QW * QH * 4 * sizeof(float4), st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return EMVS_OK;
+}
+
+template <int METHOD>
+int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix, uint32_t dimZ, const float* d_depths,
+                           float* fused, float* conf, void* idx, int idx_bytes, float* depth)
+{
+  const unsigned blocks = (n_pix + 127) / 128;
+  cudaStream_t st = ctx->stream;
+#define LAUNCH(N) \
+  k_fuse_collapse<METHOD, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth)
+  switch (A.n) {
+    case 1: k_fuse_collapse<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    case 5: LAUNCH(5); break;
+    case 6: LAUNCH(6); break;
+    case 7: LAUNCH(7); break;
+    case 8: LAUNCH(8); break;
+    default: set_error("fuse_collapse: need 1..8 grids"); return EMVS_ERR_INVALID;
+  }
+#undef LAUNCH
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EMVS_OK;
+}
+
+int launch_fuse_collapse(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix, uint32_t dimZ, const float* d_depths,
+                         float* fused, float* conf, void* idx, int idx_bytes, float* depth)
+{
+#define CASE(M) case M: return launch_fuse_collapse_n<M>(ctx, A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth)
+  switch (A.method) {
+    CASE(EMVS_FUSE_MIN);
+    CASE(EMVS_FUSE_HM);
+    CASE(EMVS_FUSE_GM);
+    CASE(EMVS_FUSE_AM);
+    CASE(EMVS_FUSE_RMS);
+    CASE(EMVS_FUSE_MAX);
+    default: set_error("Improper fusion method selected (%d)", A.method); return EMVS_ERR_INVALID;
+  }
+#undef CASE
+}
+
+// Collapse (optionally fused with an n-ary fusion) into host buffers.
+int collapse_to_host(emvs_context* ctx, const FuseArgs& A, uint32_t dimX, uint32_t dimY, uint32_t dimZ,
+                     const float* h_depths, float* fused, float* conf, void* idx, float* depth)
+{
+  REQUIRE(conf && idx, EMVS_ERR_INVALID, "collapse: conf and idx must not be NULL");
+  REQUIRE(!depth || h_depths, EMVS_ERR_INVALID, "collapse: depth output needs the depth table");
+  const uint32_t n_pix = dimX * dimY;
+  const size_t idx_sz = dimZ <= 256 ? 1 : 2;
+  const size_t off_depth = (size_t)n_pix * 4, off_idx = (size_t)n_pix * 8, off_tab = (size_t)n_pix * 10 + 16;
+  const size_t total = off_tab + (size_t)dimZ * 4;
+  int rc = grow(&ctx->d_out, &ctx->out_cap, total);
+  if (rc) return rc;
+  char* base = (char*)ctx->d_out;
+  float* d_conf = (float*)base;
+  float* d_depth = depth ? (float*)(base + off_depth) : nullptr;
+  void* d_idx = base + off_idx;
+  float* d_tab = (float*)(base + ((off_tab + 15) & ~(size_t)15));
+  cudaStream_t st = ctx->stream;
+  if (depth) CUDA_TRY(cudaMemcpyAsync(d_tab, h_depths, (size_t)dimZ * 4, cudaMemcpyHostToDevice, st));
+  rc = launch_fuse_collapse(ctx, A, n_pix, dimZ, d_tab, fused, d_conf, d_idx, (int)idx_sz, d_depth);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(conf, d_conf, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(idx, d_idx, (size_t)n_pix * idx_sz, cudaMemcpyDeviceToHost, st));
+  if (depth) CUDA_TRY(cudaMemcpyAsync(depth, d_depth, (size_t)n_pix * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return EMVS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int emvs_abi_version(void) { return EMVS_ABI_VERSION; }
+const char* emvs_last_error(void) { return g_err; }
+
+int emvs_context_create(int device, emvs_context** out)
+{
+  REQUIRE(out, EMVS_ERR_INVALID, "context_create: out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: this library has no CPU fallback");
+    return EMVS_ERR_CUDA;
+  }
+  REQUIRE(device >= 0 && device < n_dev, EMVS_ERR_INVALID, "context_create: bad device index");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return EMVS_ERR_CUDA;
+  }
+  DeviceGuard guard(device);
+  REQUIRE(guard.ok, EMVS_ERR_CUDA, "cudaSetDevice failed");
+  emvs_context* ctx = new (std::nothrow) emvs_context;
+  REQUIRE(ctx, EMVS_ERR_INVALID, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_partial, sizeof(double) * 1025);
+  if (e != cudaSuccess) {
+    set_error("context_create: %s", cudaGetErrorString(e));
+    delete ctx;
+    return EMVS_ERR_CUDA;
+  }
+  *out = ctx;
+  return EMVS_OK;
+}
+
+int emvs_context_destroy(emvs_context* ctx)
+{
+  if (!ctx) return EMVS_OK;
+  DeviceGuard guard(ctx->device);
+  if (ctx->comm) emvs_comm_destroy(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->quad);
+  cudaFree(ctx->d_events);
+  cudaFree(ctx->d_packets);
+  cudaFree(ctx->d_xy0);
+  cudaFree(ctx->d_out);
+  cudaFree(ctx->d_partial);
+  if (ctx->h_packets) cudaFreeHost(ctx->h_packets);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return EMVS_OK;
+}
+
+int emvs_context_sync(emvs_context* ctx)
+{
+  REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(ctx->device);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_context_set_slab(emvs_context* ctx, uint32_t planes)
+{
+  REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
+  ctx->slab_override = planes;
+  return EMVS_OK;
+}
+
+int emvs_context_launch_count(emvs_context* ctx, uint64_t* out)
+{
+  REQUIRE(ctx && out, EMVS_ERR_INVALID, "launch_count: NULL argument");
+  *out = ctx->launches;
+  return EMVS_OK;
+}
+
+int emvs_context_profile_vote(emvs_context* ctx, int enable)
+{
+  REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
+  ctx->profile = enable != 0;
+  ctx->prof_used = 0;
+  return EMVS_OK;
+}
+
+int emvs_context_vote_time(emvs_context* ctx, double* total_ms, uint64_t* n_launches)
+{
+  REQUIRE(ctx && total_ms && n_launches, EMVS_ERR_INVALID, "vote_time: NULL argument");
+  DeviceGuard guard(ctx->device);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  double sum = 0.;
+  for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *n_launches = ctx->prof_used / 2;
+  return EMVS_OK;
+}
+
+int emvs_context_stream(emvs_context* ctx, void** out_stream)
+{
+  REQUIRE(ctx && out_stream, EMVS_ERR_INVALID, "context_stream: NULL argument");
+  *out_stream = (void*)ctx->stream;
+  return EMVS_OK;
+}
+
+struct emvs_timer {
+  emvs_context* ctx;
+  cudaEvent_t a, b;
+};
+
+int emvs_timer_create(emvs_context* ctx, emvs_timer** out)
+{
+  REQUIRE(ctx && out, EMVS_ERR_INVALID, "timer_create: NULL argument");
+  DeviceGuard guard(ctx->device);
+  emvs_timer* t = new (std::nothrow) emvs_timer;
+  REQUIRE(t, EMVS_ERR_INVALID, "out of host memory");
+  t->ctx = ctx;
+  CUDA_TRY(cudaEventCreate(&t->a));
+  CUDA_TRY(cudaEventCreate(&t->b));
+  *out = t;
+  return EMVS_OK;
+}
+
+int emvs_timer_destroy(emvs_timer* t)
+{
+  if (!t) return EMVS_OK;
+  cudaEventDestroy(t->a);
+  cudaEventDestroy(t->b);
+  delete t;
+  return EMVS_OK;
+}
+
+int emvs_timer_start(emvs_timer* t)
+{
+  REQUIRE(t, EMVS_ERR_INVALID, "timer is NULL");
+  DeviceGuard guard(t->ctx->device);
+  CUDA_TRY(cudaEventRecord(t->a, t->ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_timer_stop(emvs_timer* t)
+{
+  REQUIRE(t, EMVS_ERR_INVALID, "timer is NULL");
+  DeviceGuard guard(t->ctx->device);
+  CUDA_TRY(cudaEventRecord(t->b, t->ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_timer_elapsed_ms(emvs_timer* t, float* ms)
+{
+  REQUIRE(t && ms, EMVS_ERR_INVALID, "timer_elapsed_ms: NULL argument");
+  DeviceGuard guard(t->ctx->device);
+  CUDA_TRY(cudaEventSynchronize(t->b));
+  CUDA_TRY(cudaEventElapsedTime(ms, t->a, t->b));
+  return EMVS_OK;
+}
+
+int emvs_host_alloc(size_t bytes, void** out)
+{
+  REQUIRE(out, EMVS_ERR_INVALID, "host_alloc: out is NULL");
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return EMVS_OK;
+}
+
+int emvs_host_free(void* p)
+{
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return EMVS_OK;
+}
+
+// ---- host geometry ---------------------------------------------------------------------------
+static int check_shape(const emvs_shape* s)
+{
+  REQUIRE(s, EMVS_ERR_INVALID, "shape is NULL");
+  REQUIRE(s->dimZ >= 1, EMVS_ERR_INVALID, "shape: dimZ must be >= 1");
+  REQUIRE(s->min_depth > 0.f, EMVS_ERR_INVALID, "shape: min_depth must be > 0");             // MAP:210
+  REQUIRE(s->max_depth > s->min_depth, EMVS_ERR_INVALID, "shape: max_depth must exceed min_depth");  // MAP:211
+  return EMVS_OK;
+}
+
+int emvs_depth_vector(const emvs_shape* shape, float* out)
+{
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  REQUIRE(out, EMVS_ERR_INVALID, "depth_vector: out is NULL");
+  host_depth_vector(*shape, out);
+  return EMVS_OK;
+}
+
+int emvs_virtual_camera(const emvs_camera* cam, const emvs_shape* shape, float out[4])
+{
+  REQUIRE(cam && shape && out, EMVS_ERR_INVALID, "virtual_camera: NULL argument");
+  host_virtual_camera(*cam, *shape, out);
+  return EMVS_OK;
+}
+
+int emvs_trajectory_pose_at(const emvs_stamped_pose* traj, size_t n, uint32_t sec, uint32_t nsec, emvs_pose* out,
+                            int* found)
+{
+  REQUIRE(traj && out && found, EMVS_ERR_INVALID, "pose_at: NULL argument");
+  REQUIRE(n >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");  // TRJ:89
+  *found = host_pose_at(traj, n, sec, nsec, out) ? 1 : 0;
+  return EMVS_OK;
+}
+
+int emvs_pose_compose(const emvs_pose* a, const emvs_pose* b, emvs_pose* out)
+{
+  REQUIRE(a && b && out, EMVS_ERR_INVALID, "pose_compose: NULL argument");
+  host_pose_compose(*a, *b, out);
+  return EMVS_OK;
+}
+
+int emvs_pose_inverse(const emvs_pose* a, emvs_pose* out)
+{
+  REQUIRE(a && out, EMVS_ERR_INVALID, "pose_inverse: NULL argument");
+  host_pose_inverse(*a, out);
+  return EMVS_OK;
+}
+
+int emvs_packetize(const emvs_event* events, size_t n_events, const emvs_stamped_pose* traj, size_t n_poses,
+                   const emvs_pose* T_rv_w, const emvs_camera* cam, const float virt[4], float z0, emvs_packet* out,
+                   size_t max_packets, size_t* n_packets)
+{
+  REQUIRE(events && traj && T_rv_w && cam && virt && n_packets, EMVS_ERR_INVALID, "packetize: NULL argument");
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  *n_packets = 0;
+  if (n_events < EMVS_PACKET_SIZE) {
+    set_error("Number of events (%zu) < packet size (%d)", n_events, EMVS_PACKET_SIZE);
+    return EMVS_ERR_TOO_FEW;
+  }
+  REQUIRE(out || max_packets == 0, EMVS_ERR_INVALID, "packetize: out is NULL");
+  *n_packets = host_packetize(events, n_events, traj, n_poses, *T_rv_w, *cam, virt, z0, out, max_packets);
+  return EMVS_OK;
+}
+
+// ---- Grid3D ----------------------------------------------------------------------------------
+int emvs_grid_create(emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ, emvs_grid** out)
+{
+  REQUIRE(ctx && out, EMVS_ERR_INVALID, "grid_create: NULL argument");
+  *out = nullptr;
+  REQUIRE(dimX && dimY && dimZ, EMVS_ERR_INVALID, "grid_create: zero dimension");
+  REQUIRE((uint64_t)dimX * dimY < (1ull << 31), EMVS_ERR_INVALID, "grid_create: plane too large");
+  DeviceGuard guard(ctx->device);
+  emvs_grid* g = new (std::nothrow) emvs_grid;
+  REQUIRE(g, EMVS_ERR_INVALID, "out of host memory");
+  g->ctx = ctx;
+  g->dimX = dimX; g->dimY = dimY; g->dimZ = dimZ;
+  g->n_cells = (size_t)dimX * dimY * dimZ;
+  cudaError_t e = cudaMalloc((void**)&g->d, g->n_cells * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->d, 0, g->n_cells * sizeof(float), ctx->stream);
+  if (e != cudaSuccess) {
+    set_error("grid_create: %s", cudaGetErrorString(e));
+    delete g;
+    return EMVS_ERR_CUDA;
+  }
+  *out = g;
+  return EMVS_OK;
+}
+
+int emvs_grid_destroy(emvs_grid* g)
+{
+  if (!g) return EMVS_OK;
+  DeviceGuard guard(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  cudaFree(g->d);
+  delete g;
+  return EMVS_OK;
+}
+
+int emvs_grid_dims(const emvs_grid* g, uint32_t* dimX, uint32_t* dimY, uint32_t* dimZ)
+{
+  REQUIRE(g, EMVS_ERR_INVALID, "grid is NULL");
+  if (dimX) *dimX = g->dimX;
+  if (dimY) *dimY = g->dimY;
+  if (dimZ) *dimZ = g->dimZ;
+  return EMVS_OK;
+}
+
+int emvs_grid_reset(emvs_grid* g)
+{
+  REQUIRE(g, EMVS_ERR_INVALID, "grid is NULL");
+  DeviceGuard guard(g->ctx->device);
+  CUDA_TRY(cudaMemsetAsync(g->d, 0, g->n_cells * sizeof(float), g->ctx->stream));
+  return EMVS_OK;
+}
+
+static bool same_dims(const emvs_grid* a, const emvs_grid* b)
+{
+  return a->dimX == b->dimX && a->dimY == b->dimY && a->dimZ == b->dimZ && a->ctx == b->ctx;
+}
+
+int emvs_grid_op(emvs_grid* a, const emvs_grid* b, int op, int n, float eps)
+{
+  REQUIRE(a, EMVS_ERR_INVALID, "grid_op: a is NULL");
+  REQUIRE(op >= EMVS_OP_ADD && op <= EMVS_OP_AM_FROM_SUM, EMVS_ERR_INVALID, "grid_op: unknown op");
+  const bool unary = op == EMVS_OP_HM_FROM_SUMINV || op == EMVS_OP_AM_FROM_SUM;
+  REQUIRE(unary || b, EMVS_ERR_INVALID, "grid_op: b is NULL");
+  REQUIRE(unary || same_dims(a, b), EMVS_ERR_INVALID, "grid_op: grids differ in shape or context");
+  emvs_context* ctx = a->ctx;
+  DeviceGuard guard(ctx->device);
+  const unsigned blocks = (unsigned)std::min<size_t>((a->n_cells + 255) / 256, (size_t)ctx->sm_count * 16);
+  k_grid_op<<<blocks, 256, 0, ctx->stream>>>(a->d, unary ? nullptr : b->d, a->n_cells, op, n, eps);
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EMVS_OK;
+}
+
+int emvs_grid_copy(emvs_grid* dst, const emvs_grid* src)
+{
+  REQUIRE(dst && src, EMVS_ERR_INVALID, "grid_copy: NULL argument");
+  REQUIRE(same_dims(dst, src), EMVS_ERR_INVALID, "grid_copy: grids differ in shape or context");
+  DeviceGuard guard(dst->ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(dst->d, src->d, dst->n_cells * sizeof(float), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_grid_download(const emvs_grid* g, float* host_out)
+{
+  REQUIRE(g && host_out, EMVS_ERR_INVALID, "grid_download: NULL argument");
+  DeviceGuard guard(g->ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(host_out, g->d, g->n_cells * sizeof(float), cudaMemcpyDeviceToHost, g->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_grid_upload(emvs_grid* g, const float* host_in)
+{
+  REQUIRE(g && host_in, EMVS_ERR_INVALID, "grid_upload: NULL argument");
+  DeviceGuard guard(g->ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(g->d, host_in, g->n_cells * sizeof(float), cudaMemcpyHostToDevice, g->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_grid_mean_square(const emvs_grid* g, double* out)
+{
+  REQUIRE(g && out, EMVS_ERR_INVALID, "grid_mean_square: NULL argument");
+  emvs_context* ctx = g->ctx;
+  DeviceGuard guard(ctx->device);
+  const int blocks = (int)std::min<size_t>((g->n_cells + 255) / 256, 1024);
+  k_sumsq_partial<<<blocks, 256, 0, ctx->stream>>>(g->d, g->n_cells, ctx->d_partial);
+  k_sumsq_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partial, blocks, ctx->d_partial + 1024);
+  ctx->launches += 2;
+  double sum = 0.;
+  CUDA_TRY(cudaMemcpyAsync(&sum, ctx->d_partial + 1024, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *out = sum / (double)g->n_cells;
+  return EMVS_OK;
+}
+
+int emvs_grid_collapse_max(const emvs_grid* g, const float* depths, float* conf, void* idx, float* depth)
+{
+  REQUIRE(g, EMVS_ERR_INVALID, "grid is NULL");
+  DeviceGuard guard(g->ctx->device);
+  FuseArgs A{};
+  A.g[0] = g->d;
+  A.n = 1;
+  A.method = EMVS_FUSE_MAX;
+  return collapse_to_host(g->ctx, A, g->dimX, g->dimY, g->dimZ, depths, nullptr, conf, idx, depth);
+}
+
+int emvs_fuse_collapse(emvs_grid* const* grids, int n, int method, const float* depths, emvs_grid* fused_out,
+                       float* conf, void* idx, float* depth)
+{
+  REQUIRE(grids && n >= 1 && n <= kMaxFuse, EMVS_ERR_INVALID, "fuse_collapse: need 1..8 grids");
+  REQUIRE(method >= EMVS_FUSE_MIN && method <= EMVS_FUSE_MAX, EMVS_ERR_INVALID, "Improper fusion method selected");
+  FuseArgs A{};
+  A.n = n;
+  A.method = method;
+  for (int i = 0; i < n; ++i) {
+    REQUIRE(grids[i], EMVS_ERR_INVALID, "fuse_collapse: NULL grid");
+    REQUIRE(same_dims(grids[0], grids[i]), EMVS_ERR_INVALID, "fuse_collapse: grids differ in shape or context");
+    A.g[i] = grids[i]->d;
+  }
+  REQUIRE(!fused_out || same_dims(grids[0], fused_out), EMVS_ERR_INVALID, "fuse_collapse: fused_out shape mismatch");
+  const emvs_grid* g = grids[0];
+  DeviceGuard guard(g->ctx->device);
+  return collapse_to_host(g->ctx, A, g->dimX, g->dimY, g->dimZ, depths, fused_out ? fused_out->d : nullptr, conf, idx,
+                          depth);
+}
+
+int emvs_fuse_collapse_device(emvs_grid* const* grids, int n, int method, const float* d_depths, emvs_grid* fused_out,
+                              float* d_conf, void* d_idx, float* d_depth)
+{
+  REQUIRE(grids && n >= 1 && n <= kMaxFuse, EMVS_ERR_INVALID, "fuse_collapse: need 1..8 grids");
+  REQUIRE(method >= EMVS_FUSE_MIN && method <= EMVS_FUSE_MAX, EMVS_ERR_INVALID, "Improper fusion method selected");
+  REQUIRE(d_conf && d_idx, EMVS_ERR_INVALID, "fuse_collapse_device: conf and idx must not be NULL");
+  REQUIRE(!d_depth || d_depths, EMVS_ERR_INVALID, "fuse_collapse_device: depth output needs the depth table");
+  FuseArgs A{};
+  A.n = n;
+  A.method = method;
+  for (int i = 0; i < n; ++i) {
+    REQUIRE(grids[i], EMVS_ERR_INVALID, "fuse_collapse: NULL grid");
+    REQUIRE(same_dims(grids[0], grids[i]), EMVS_ERR_INVALID, "fuse_collapse: grids differ in shape or context");
+    A.g[i] = grids[i]->d;
+  }
+  REQUIRE(!fused_out || same_dims(grids[0], fused_out), EMVS_ERR_INVALID, "fuse_collapse: fused_out shape mismatch");
+  const emvs_grid* g = grids[0];
+  DeviceGuard guard(g->ctx->device);
+  return launch_fuse_collapse(g->ctx, A, g->dimX * g->dimY, g->dimZ, d_depths, fused_out ? fused_out->d : nullptr,
+                              d_conf, d_idx, g->dimZ <= 256 ? 1 : 2, d_depth);
+}
+
+int emvs_grid_device_ptr(const emvs_grid* g, void** out)
+{
+  REQUIRE(g && out, EMVS_ERR_INVALID, "grid_device_ptr: NULL argument");
+  *out = g->d;
+  return EMVS_OK;
+}
+
+// ---- MapperEMVS ------------------------------------------------------------------------------
+int emvs_mapper_create(emvs_context* ctx, const emvs_camera* cam, const emvs_shape* shape, emvs_mapper** out)
+{
+  REQUIRE(ctx && cam && out, EMVS_ERR_INVALID, "mapper_create: NULL argument");
+  *out = nullptr;
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  REQUIRE(cam->width && cam->height, EMVS_ERR_INVALID, "mapper_create: empty sensor");
+  REQUIRE(cam->width <= 65536 && cam->height <= 65536, EMVS_ERR_INVALID, "mapper_create: sensor exceeds uint16 event coordinates");
+  // geometry_utils.hpp:36-41 CHECKs on the virtual camera
+  REQUIRE(cam->fx > 0.f && cam->fy > 0.f && cam->cx > 0.f && cam->cy > 0.f, EMVS_ERR_INVALID,
+          "mapper_create: fx, fy, cx, cy must be > 0");
+  DeviceGuard guard(ctx->device);
+  emvs_mapper* m = new (std::nothrow) emvs_mapper;
+  REQUIRE(m, EMVS_ERR_INVALID, "out of host memory");
+  m->ctx = ctx;
+  m->cam = *cam;
+  m->shape = *shape;
+  if (!m->shape.dimX) m->shape.dimX = cam->width;    // MAP:216
+  if (!m->shape.dimY) m->shape.dimY = cam->height;   // MAP:217
+  host_virtual_camera(*cam, m->shape, m->virt);
+  m->depths.resize(shape->dimZ);
+  host_depth_vector(m->shape, m->depths.data());
+  rc = emvs_grid_create(ctx, m->shape.dimX, m->shape.dimY, m->shape.dimZ, &m->grid);
+  if (rc) { delete m; return rc; }
+  cudaError_t e = cudaMalloc((void**)&m->d_depths, sizeof(float) * shape->dimZ);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_depths, m->depths.data(), sizeof(float) * shape->dimZ, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_lut, sizeof(float2) * (size_t)cam->width * cam->height);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_counts, sizeof(unsigned long long) * shape->dimZ);
+  if (e == cudaSuccess) e = cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned long long) * shape->dimZ, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    set_error("mapper_create: %s", cudaGetErrorString(e));
+    emvs_mapper_destroy(m);
+    return EMVS_ERR_CUDA;
+  }
+  *out = m;
+  return EMVS_OK;
+}
+
+int emvs_mapper_destroy(emvs_mapper* m)
+{
+  if (!m) return EMVS_OK;
+  DeviceGuard guard(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  emvs_grid_destroy(m->grid);
+  cudaFree(m->d_depths);
+  cudaFree(m->d_lut);
+  cudaFree(m->d_counts);
+  delete m;
+  return EMVS_OK;
+}
+
+int emvs_mapper_set_lut(emvs_mapper* m, const float* lut_xy, size_t n_pixels)
+{
+  REQUIRE(m && lut_xy, EMVS_ERR_INVALID, "set_lut: NULL argument");
+  REQUIRE(n_pixels == (size_t)m->cam.width * m->cam.height, EMVS_ERR_INVALID, "set_lut: size must be width*height");
+  DeviceGuard guard(m->ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(m->d_lut, lut_xy, n_pixels * sizeof(float2), cudaMemcpyHostToDevice, m->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+  m->lut_set = true;
+  return EMVS_OK;
+}
+
+int emvs_mapper_shape(const emvs_mapper* m, emvs_shape* shape_out, float virt_out[4])
+{
+  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
+  if (shape_out) *shape_out = m->shape;
+  if (virt_out) memcpy(virt_out, m->virt, sizeof m->virt);
+  return EMVS_OK;
+}
+
+int emvs_mapper_depths(const emvs_mapper* m, float* out)
+{
+  REQUIRE(m && out, EMVS_ERR_INVALID, "mapper_depths: NULL argument");
+  memcpy(out, m->depths.data(), m->depths.size() * sizeof(float));
+  return EMVS_OK;
+}
+
+int emvs_mapper_depths_device(const emvs_mapper* m, const float** out)
+{
+  REQUIRE(m && out, EMVS_ERR_INVALID, "mapper_depths_device: NULL argument");
+  *out = m->d_depths;
+  return EMVS_OK;
+}
+
+int emvs_mapper_grid(emvs_mapper* m, emvs_grid** out)
+{
+  REQUIRE(m && out, EMVS_ERR_INVALID, "mapper_grid: NULL argument");
+  *out = m->grid;
+  return EMVS_OK;
+}
+
+static int check_packets(const emvs_packet* pk, size_t n_packets, size_t n_events)
+{
+  for (size_t j = 0; j < n_packets; ++j)
+    if (pk[j].first_event + EMVS_PACKET_SIZE > n_events) {
+      set_error("packet %zu reaches past the event list (first_event=%llu, n_events=%zu)", j,
+                (unsigned long long)pk[j].first_event, n_events);
+      return EMVS_ERR_INVALID;
+    }
+  return EMVS_OK;
+}
+
+int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
+                      size_t n_packets, int flags)
+{
+  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
+  REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE(n_packets == 0 || (events && packets), EMVS_ERR_INVALID, "mapper_build: NULL events/packets");
+  int rc = check_packets(packets, n_packets, n_events);
+  if (rc) return rc;
+  emvs_context* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  if (n_packets) {
+    // Only the span of events that packets reference has to travel.
+    size_t last = 0;
+    for (size_t j = 0; j < n_packets; ++j) last = std::max<size_t>(last, packets[j].first_event + EMVS_PACKET_SIZE);
+    rc = grow(&ctx->d_events, &ctx->events_cap, n_events * sizeof(emvs_event));
+    if (rc) return rc;
+    rc = grow(&ctx->d_packets, &ctx->packets_cap, n_packets * sizeof(emvs_packet));
+    if (rc) return rc;
+    size_t lo = n_events;
+    for (size_t j = 0; j < n_packets; ++j) lo = std::min<size_t>(lo, packets[j].first_event);
+    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + lo, events + lo, (last - lo) * sizeof(emvs_event),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_packets, packets, n_packets * sizeof(emvs_packet), cudaMemcpyHostToDevice,
+                             ctx->stream));
+  }
+  rc = build_on_device(m, (const emvs_event*)ctx->d_events, n_events, (const emvs_packet*)ctx->d_packets, n_packets,
+                       flags);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_events, const void* d_packets,
+                             size_t n_packets, int flags)
+{
+  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
+  REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build_device: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE(n_packets == 0 || (d_events && d_packets), EMVS_ERR_INVALID, "mapper_build_device: NULL events/packets");
+  DeviceGuard guard(m->ctx->device);
+  return build_on_device(m, (const emvs_event*)d_events, n_events, (const emvs_packet*)d_packets, n_packets, flags);
+}
+
+int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                             const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w)
+{
+  REQUIRE(m && events && traj && T_rv_w, EMVS_ERR_INVALID, "evaluate_dsi: NULL argument");
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  if (n_events < EMVS_PACKET_SIZE) {
+    set_error("Number of events (%zu) < packet size (%d)", n_events, EMVS_PACKET_SIZE);
+    return EMVS_ERR_TOO_FEW;
+  }
+  emvs_context* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  const size_t max_pk = n_events / EMVS_PACKET_SIZE + 1;
+  if (max_pk > ctx->h_packets_cap) {
+    if (ctx->h_packets) CUDA_TRY(cudaFreeHost(ctx->h_packets));
+    ctx->h_packets = nullptr;
+    ctx->h_packets_cap = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&ctx->h_packets, max_pk * sizeof(emvs_packet), cudaHostAllocDefault));
+    ctx->h_packets_cap = max_pk;
+  }
+  const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
+                                     ctx->h_packets, max_pk);
+  return emvs_mapper_build(m, events, n_events, ctx->h_packets, n_pk, EMVS_BUILD_RESET);
+}
+
+int emvs_mapper_counts(const emvs_mapper* m, uint64_t* per_plane)
+{
+  REQUIRE(m && per_plane, EMVS_ERR_INVALID, "mapper_counts: NULL argument");
+  DeviceGuard guard(m->ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(per_plane, m->d_counts, sizeof(uint64_t) * m->shape.dimZ, cudaMemcpyDeviceToHost,
+                           m->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+  return EMVS_OK;
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------
+#define NCCL_TRY(api, expr)                                                          \
+  do {                                                                               \
+    int r_ = (expr);                                                                 \
+    if (r_ != 0) {                                                                   \
+      set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, (api)->GetErrorString(r_)); \
+      return EMVS_ERR_NCCL;                                                          \
+    }                                                                                \
+  } while (0)
+
+int emvs_comm_unique_id(uint8_t out_id[128])
+{
+  REQUIRE(out_id, EMVS_ERR_INVALID, "comm_unique_id: NULL argument");
+  const NcclApi* api = nccl_api();
+  if (!api) return EMVS_ERR_NCCL;
+  NcclId id;
+  NCCL_TRY(api, api->GetUniqueId(&id));
+  memcpy(out_id, id.b, 128);
+  return EMVS_OK;
+}
+
+int emvs_comm_init(emvs_context* ctx, const uint8_t id_bytes[128], int n_ranks, int rank)
+{
+  REQUIRE(ctx && id_bytes, EMVS_ERR_INVALID, "comm_init: NULL argument");
+  REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, EMVS_ERR_INVALID, "comm_init: bad rank / n_ranks");
+  REQUIRE(!ctx->comm, EMVS_ERR_STATE, "comm_init: communicator already initialised");
+  const NcclApi* api = nccl_api();
+  if (!api) return EMVS_ERR_NCCL;
+  DeviceGuard guard(ctx->device);
+  NcclId id;
+  memcpy(id.b, id_bytes, 128);
+  NCCL_TRY(api, api->CommInitRank(&ctx->comm, n_ranks, id, rank));
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  return EMVS_OK;
+}
+
+int emvs_comm_destroy(emvs_context* ctx)
+{
+  REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
+  if (!ctx->comm) return EMVS_OK;
+  const NcclApi* api = nccl_api();
+  if (!api) return EMVS_ERR_NCCL;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  api->CommDestroy(ctx->comm);
+  ctx->comm = nullptr;
+  ctx->n_ranks = 1;
+  ctx->rank = 0;
+  return EMVS_OK;
+}
+
+int emvs_grid_allreduce(emvs_grid* g)
+{
+  const int rc = emvs_grid_allreduce_async(g);
+  if (rc) return rc;
+  DeviceGuard guard(g->ctx->device);
+  CUDA_TRY(cudaStreamSynchronize(g->ctx->stream));
+  return EMVS_OK;
+}
+
+int emvs_grid_allreduce_async(emvs_grid* g)
+{
+  REQUIRE(g, EMVS_ERR_INVALID, "grid is NULL");
+  emvs_context* ctx = g->ctx;
+  REQUIRE(ctx->comm, EMVS_ERR_STATE, "grid_allreduce: communicator not initialised (emvs_comm_init)");
+  const NcclApi* api = nccl_api();
+  if (!api) return EMVS_ERR_NCCL;
+  DeviceGuard guard(ctx->device);
+  // chunk by Z-slab so the ring pipeline starts on the first planes while later ones queue
+  const size_t plane = (size_t)g->dimX * g->dimY;
+  const size_t planes_per_chunk = std::max<size_t>(1, ((size_t)64 << 20) / (plane * sizeof(float)));
+  NCCL_TRY(api, api->GroupStart());
+  for (size_t k = 0; k < g->dimZ; k += planes_per_chunk) {
+    const size_t nk = std::min(planes_per_chunk, (size_t)g->dimZ - k);
+    float* p = g->d + k * plane;
+    NCCL_TRY(api, api->AllReduce(p, p, nk * plane, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ctx->comm, (void*)ctx->stream));
+  }
+  NCCL_TRY(api, api->GroupEnd());
+  return EMVS_OK;
+}
+
+int emvs_mapper_counts_allreduce(emvs_mapper* m)
+{
+  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
+  emvs_context* ctx = m->ctx;
+  REQUIRE(ctx->comm, EMVS_ERR_STATE, "counts_allreduce: communicator not initialised (emvs_comm_init)");
+  const NcclApi* api = nccl_api();
+  if (!api) return EMVS_ERR_NCCL;
+  DeviceGuard guard(ctx->device);
+  NCCL_TRY(api, api->AllReduce(m->d_counts, m->d_counts, m->shape.dimZ, /*ncclUint64*/ 5, /*ncclSum*/ 0, ctx->comm,
+                               (void*)ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return EMVS_OK;
+}
+
+}  // extern "C"

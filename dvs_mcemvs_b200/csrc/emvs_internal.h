@@ -1,0 +1,43 @@
+// emvs_internal.h — declarations shared by the translation units of libemvs_b200.so.
+#ifndef EMVS_INTERNAL_H_
+#define EMVS_INTERNAL_H_
+
+#include "emvs_b200.h"
+
+#include <cstddef>
+#include <cstdint>
+
+namespace emvs {
+
+// thread-local error message behind emvs_last_error()
+void set_error(const char* fmt, ...);
+
+// host_geometry.cpp
+void host_depth_vector(const emvs_shape& shape, float* out);
+void host_virtual_camera(const emvs_camera& cam, const emvs_shape& shape, float out[4]);
+bool host_pose_at(const emvs_stamped_pose* traj, size_t n, uint32_t sec, uint32_t nsec, emvs_pose* out);
+void host_pose_compose(const emvs_pose& a, const emvs_pose& b, emvs_pose* out);
+void host_pose_inverse(const emvs_pose& a, emvs_pose* out);
+size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+                      const emvs_pose& T_rv_w, const emvs_camera& cam, const float virt[4], float z0,
+                      emvs_packet* out, size_t max_out);
+
+// nccl_dl.cpp — NCCL resolved at run time so the library loads (and every single-GPU entry
+// point works) on machines without NCCL, and shares torch's NCCL when loaded from Python.
+struct NcclId {  // ncclUniqueId (NCCL_UNIQUE_ID_BYTES == 128), passed by value
+  char b[128];
+};
+struct NcclApi {
+  int (*GetUniqueId)(NcclId* id);
+  int (*CommInitRank)(void** comm, int nranks, NcclId id, int rank);
+  int (*CommDestroy)(void* comm);
+  int (*AllReduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, void* stream);
+  int (*GroupStart)(void);
+  int (*GroupEnd)(void);
+  const char* (*GetErrorString)(int);
+};
+const NcclApi* nccl_api();  // nullptr when libnccl cannot be loaded (error set)
+
+}  // namespace emvs
+
+#endif

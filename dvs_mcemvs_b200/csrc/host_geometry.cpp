@@ -1,0 +1,266 @@
+// host_geometry.cpp — host half of the mapping path: depth sampling, virtual camera, SE(3)
+// trajectory interpolation and the per-packet homography stage of MapperEMVS::evaluateDSI.
+// One pose + one 3x3 inverse per 1024 events, so it stays on the host.
+//
+// Reference behaviour (paths relative to the reference root):
+//   depth tables        mapper_emvs_stereo/include/mapper_emvs_stereo/depth_vector.hpp:88-103,131-148
+//   virtual camera      mapper_emvs_stereo/src/mapper_emvs_stereo.cpp:208-241
+//   pinhole K, K^-1     mapper_emvs_stereo/include/mapper_emvs_stereo/geometry_utils.hpp:28-48
+//   pose interpolation  mapper_emvs_stereo/include/mapper_emvs_stereo/trajectory.hpp:92-127
+//   packet stage        mapper_emvs_stereo/src/mapper_emvs_stereo.cpp:67-126
+// minkindr (SE(3)) and Eigen (3x3 float algebra) are external to the reference tree; their
+// arithmetic is restated here (see DESIGN.md "Third-party arithmetic").
+//
+// Compiled with -ffp-contract=off: the float chain must not be contracted into FMAs, the
+// device kernels consume these bits and the oracle recomputes them.
+
+#include "emvs_internal.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace emvs {
+namespace {
+
+// ---- small fixed-size float algebra with Eigen's evaluation order ----------------------------
+struct Mat3f {
+  float m[3][3];
+};
+
+inline Mat3f operator*(const Mat3f& a, const Mat3f& b)
+{
+  Mat3f r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float s = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j];
+      s = s + a.m[i][2] * b.m[2][j];
+      r.m[i][j] = s;
+    }
+  return r;
+}
+
+inline float minor2(const Mat3f& a, int r, int c)
+{
+  const int r1 = (r + 1) % 3, r2 = (r + 2) % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+  return a.m[r1][c1] * a.m[r2][c2] - a.m[r1][c2] * a.m[r2][c1];
+}
+
+// Cofactor inverse: adj(A)/det(A), determinant expanded along column 0, one reciprocal.
+inline Mat3f inverse(const Mat3f& a)
+{
+  float cof[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) cof[r][c] = minor2(a, r, c);
+  float det = cof[0][0] * a.m[0][0] + cof[1][0] * a.m[1][0];
+  det = det + cof[2][0] * a.m[2][0];
+  const float inv_det = 1.f / det;
+  Mat3f out;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out.m[r][c] = cof[c][r] * inv_det;
+  return out;
+}
+
+inline Mat3f pinhole_K(float fx, float fy, float cx, float cy)
+{
+  Mat3f K = {{{fx, 0.f, cx}, {0.f, fy, cy}, {0.f, 0.f, 1.f}}};
+  return K;
+}
+
+// ---- SE(3) in double, quaternion (w, x, y, z) -------------------------------------------------
+struct Vec3 {
+  double x, y, z;
+};
+inline Vec3 cross(const Vec3& a, const Vec3& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+struct Quat {
+  double w, x, y, z;
+  Vec3 vec() const { return {x, y, z}; }
+  Quat conj() const { return {w, -x, -y, -z}; }
+  Quat operator*(const Quat& o) const
+  {
+    return {w * o.w - x * o.x - y * o.y - z * o.z,
+            w * o.x + x * o.w + y * o.z - z * o.y,
+            w * o.y + y * o.w + z * o.x - x * o.z,
+            w * o.z + z * o.w + x * o.y - y * o.x};
+  }
+  // v' = v + w*uv + q_v x uv with uv = 2 (q_v x v)
+  Vec3 rotate(const Vec3& v) const
+  {
+    Vec3 uv = cross(vec(), v);
+    uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
+    const Vec3 c = cross(vec(), uv);
+    return {v.x + w * uv.x + c.x, v.y + w * uv.y + c.y, v.z + w * uv.z + c.z};
+  }
+  void to_matrix(double R[3][3]) const
+  {
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0][0] = 1 - (tyy + tzz); R[0][1] = txy - twz;       R[0][2] = txz + twy;
+    R[1][0] = txy + twz;       R[1][1] = 1 - (txx + tzz); R[1][2] = tyz - twx;
+    R[2][0] = txz - twy;       R[2][1] = tyz + twx;       R[2][2] = 1 - (txx + tyy);
+  }
+};
+
+const double kEps4thRoot = 1.220703125e-4;  // DBL_EPSILON^(1/4)
+
+inline double asin_over_x(double x) { return std::fabs(x) < kEps4thRoot ? 1.0 + x * x * (1.0 / 6.0) : std::asin(x) / x; }
+
+// rotation vector of a unit quaternion, log(-q) == log(q)
+inline Vec3 quat_log(const Quat& q)
+{
+  const double na = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  double scale;
+  if (std::fabs(q.w) < na) scale = q.w >= 0 ? std::acos(q.w) / na : -std::acos(-q.w) / na;
+  else scale = q.w > 0 ? asin_over_x(na) : -asin_over_x(na);
+  const double s2 = 2.0 * scale;
+  return {q.x * s2, q.y * s2, q.z * s2};
+}
+
+inline Quat quat_exp(const Vec3& r)
+{
+  const double theta = std::sqrt(r.x * r.x + r.y * r.y + r.z * r.z);
+  const double na = theta < kEps4thRoot ? 0.5 - theta * theta * (1.0 / 48.0) : std::sin(theta * 0.5) / theta;
+  return {std::cos(theta * 0.5), r.x * na, r.y * na, r.z * na};
+}
+
+struct SE3 {
+  Quat q;
+  Vec3 t;
+  SE3 operator*(const SE3& o) const
+  {
+    const Vec3 r = q.rotate(o.t);
+    return {q * o.q, {t.x + r.x, t.y + r.y, t.z + r.z}};
+  }
+  SE3 inverse() const
+  {
+    const Quat qi = q.conj();
+    const Vec3 r = qi.rotate(t);
+    return {qi, {-r.x, -r.y, -r.z}};
+  }
+};
+
+inline SE3 load(const emvs_pose& p) { return {{p.q[0], p.q[1], p.q[2], p.q[3]}, {p.t[0], p.t[1], p.t[2]}}; }
+inline void store(const SE3& s, emvs_pose* p)
+{
+  p->q[0] = s.q.w; p->q[1] = s.q.x; p->q[2] = s.q.y; p->q[3] = s.q.z;
+  p->t[0] = s.t.x; p->t[1] = s.t.y; p->t[2] = s.t.z;
+}
+
+// ros::Time ordering and ros::Duration::toSec()
+inline bool before(uint32_t as, uint32_t an, uint32_t bs, uint32_t bn) { return as != bs ? as < bs : an < bn; }
+inline double seconds_between(uint32_t as, uint32_t an, uint32_t bs, uint32_t bn)  // a - b
+{
+  int64_t s = (int64_t)as - (int64_t)bs;
+  int64_t n = (int64_t)an - (int64_t)bn;
+  if (n < 0) { n += 1000000000LL; s -= 1; }
+  if (n >= 1000000000LL) { n -= 1000000000LL; s += 1; }
+  return (double)s + 1e-9 * (double)n;
+}
+
+bool interpolate(const emvs_stamped_pose* traj, size_t n, uint32_t sec, uint32_t nsec, SE3* out)
+{
+  // first control pose strictly after t
+  size_t lo = 0, hi = n;
+  while (lo < hi) {
+    const size_t mid = lo + (hi - lo) / 2;
+    if (before(sec, nsec, traj[mid].sec, traj[mid].nsec)) hi = mid; else lo = mid + 1;
+  }
+  if (lo == 0 || lo == n) return false;  // no extrapolation, past or future
+  const emvs_stamped_pose& p0 = traj[lo - 1];
+  const emvs_stamped_pose& p1 = traj[lo];
+  const SE3 T0 = load(p0.T), T1 = load(p1.T);
+  const SE3 rel = T0.inverse() * T1;
+  const double s = seconds_between(sec, nsec, p0.sec, p0.nsec) / seconds_between(p1.sec, p1.nsec, p0.sec, p0.nsec);
+  const Vec3 w = quat_log(rel.q);
+  const SE3 step = {quat_exp({s * w.x, s * w.y, s * w.z}), {s * rel.t.x, s * rel.t.y, s * rel.t.z}};
+  *out = T0 * step;
+  return true;
+}
+
+}  // namespace
+
+// ---- exported host helpers --------------------------------------------------------------------
+
+void host_depth_vector(const emvs_shape& sh, float* out)
+{
+  float zmin = sh.min_depth, zmax = sh.max_depth;
+  if (zmin > zmax) { const float t = zmin; zmin = zmax; zmax = t; }
+  const size_t nz = sh.dimZ;
+  if (!sh.inverse_depth) {
+    const float mult = (float)(nz / (zmax - zmin));
+    for (size_t i = 0; i < nz; ++i) out[i] = zmin + (float)i / mult;
+  } else {
+    const float rho_near = 1.f / zmin, rho_far = 1.f / zmax;
+    const float mult = (float)(nz / (rho_near - rho_far));
+    for (size_t i = 0; i < nz; ++i) out[i] = 1.f / (rho_far + (float)i / mult);
+  }
+}
+
+void host_virtual_camera(const emvs_camera& cam, const emvs_shape& sh, float out[4])
+{
+  const uint32_t dimX = sh.dimX ? sh.dimX : cam.width;
+  float f;
+  if (sh.fov_deg < 10.f) {
+    f = cam.fx;
+  } else {
+    const float fov_rad = sh.fov_deg * 3.1415926535897932384626433832795 / 180.0;
+    f = 0.5 * (float)dimX / std::tan(0.5 * fov_rad);
+  }
+  out[0] = f; out[1] = f; out[2] = cam.cx; out[3] = cam.cy;  // principal point of the real camera
+}
+
+bool host_pose_at(const emvs_stamped_pose* traj, size_t n, uint32_t sec, uint32_t nsec, emvs_pose* out)
+{
+  SE3 T;
+  if (!interpolate(traj, n, sec, nsec, &T)) return false;
+  store(T, out);
+  return true;
+}
+
+void host_pose_compose(const emvs_pose& a, const emvs_pose& b, emvs_pose* out) { store(load(a) * load(b), out); }
+void host_pose_inverse(const emvs_pose& a, emvs_pose* out) { store(load(a).inverse(), out); }
+
+size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+                      const emvs_pose& T_rv_w_pod, const emvs_camera& cam, const float virt[4], float z0,
+                      emvs_packet* out, size_t max_out)
+{
+  const Mat3f K = pinhole_K(cam.fx, cam.fy, cam.cx, cam.cy);
+  const Mat3f Kinv_virtual = inverse(pinhole_K(virt[0], virt[1], virt[2], virt[3]));
+  const SE3 T_rv_w = load(T_rv_w_pod);
+  size_t produced = 0;
+  size_t cur = 0;
+  while (cur + EMVS_PACKET_SIZE < n_ev && produced < max_out) {
+    const emvs_event& mid = ev[cur + EMVS_PACKET_SIZE / 2];
+    SE3 T_w_ev;
+    if (!interpolate(traj, n_poses, mid.sec, mid.nsec, &T_w_ev)) {
+      ++cur;  // drop one event and retry
+      continue;
+    }
+    const SE3 T_ev_rv = (T_rv_w * T_w_ev).inverse();
+    double Rd[3][3];
+    T_ev_rv.q.to_matrix(Rd);
+    Mat3f R;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R.m[i][j] = (float)Rd[i][j];
+    const float t[3] = {(float)T_ev_rv.t.x, (float)T_ev_rv.t.y, (float)T_ev_rv.t.z};
+
+    emvs_packet& pk = out[produced++];
+    pk.first_event = cur;
+    for (int i = 0; i < 3; ++i) {  // C = -R^T t
+      float s = (-R.m[0][i]) * t[0] + (-R.m[1][i]) * t[1];
+      pk.C[i] = s + (-R.m[2][i]) * t[2];
+    }
+    Mat3f Hinv = R;  // (H_z0)^-1 = z0 R + t e3^T
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Hinv.m[i][j] *= z0;
+    for (int i = 0; i < 3; ++i) Hinv.m[i][2] += t[i];
+    const Mat3f H = inverse((K * Hinv) * Kinv_virtual);
+    std::memcpy(pk.H, H.m, sizeof pk.H);
+    cur += EMVS_PACKET_SIZE;
+  }
+  return produced;
+}
+
+}  // namespace emvs

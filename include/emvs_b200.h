@@ -1,0 +1,262 @@
+/* emvs_b200.h — C-ABI of the B200-native DSI ray-voting engine.
+ *
+ * This is the drop-in boundary for the mapping hot path of tub-rip/dvs_mcemvs.  The
+ * reference has no FFI layer: its boundary is the C++ class API of libcartesian3dgrid
+ * (class Grid3D) and libmapper_emvs_stereo (class EMVS::MapperEMVS).  The header-only host
+ * classes in dvs_mcemvs_b200/host/ keep those class names and signatures and forward to the
+ * entry points below; every entry point cites the reference interface it replaces
+ * (paths relative to the reference root):
+ *   MAP = mapper_emvs_stereo/src/mapper_emvs_stereo.cpp
+ *   MHP = mapper_emvs_stereo/include/mapper_emvs_stereo/mapper_emvs_stereo.hpp
+ *   G3H = cartesian3dgrid/include/cartesian3dgrid/cartesian3dgrid.h
+ *   G3C = cartesian3dgrid/src/cartesian3dgrid.cpp
+ *   DV  = mapper_emvs_stereo/include/mapper_emvs_stereo/depth_vector.hpp
+ *   TRJ = mapper_emvs_stereo/include/mapper_emvs_stereo/trajectory.hpp
+ *   P1/P2 = mapper_emvs_stereo/src/process1.cpp / process2.cpp
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (EMVS_OK == 0) and never throws or aborts across the boundary; emvs_last_error() gives the
+ * message of the last failure on the calling thread.  There is NO CPU fallback: every compute
+ * entry point needs a CUDA device of compute capability 10.x and fails with EMVS_ERR_CUDA
+ * otherwise.  Calls on one context are serialised by the caller (the reference's evaluateDSI
+ * is not re-entrant either, MAP:79,83); different contexts may be driven from different
+ * threads.  Unless a function says otherwise, pointer arguments are HOST pointers that are
+ * only borrowed for the duration of the call, and the call returns after the work is complete.
+ */
+#ifndef EMVS_B200_H_
+#define EMVS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMVS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define EMVS_API __attribute__((visibility("default")))
+#else
+#define EMVS_API
+#endif
+
+/* ---- status codes -------------------------------------------------------------------- */
+enum {
+  EMVS_OK = 0,
+  EMVS_ERR_INVALID = 1,     /* bad argument (null pointer, shape mismatch, bad id)          */
+  EMVS_ERR_CUDA = 2,        /* CUDA runtime error or no usable device                       */
+  EMVS_ERR_TOO_FEW = 3,     /* fewer than EMVS_PACKET_SIZE events: evaluateDSI -> false (MAP:71-75) */
+  EMVS_ERR_NCCL = 4,        /* NCCL unavailable or a collective failed                      */
+  EMVS_ERR_STATE = 5        /* call sequence error (e.g. LUT not set, comm not initialised) */
+};
+
+#define EMVS_PACKET_SIZE 1024 /* MHP:153 packet_size_ */
+
+/* ---- POD types ------------------------------------------------------------------------ */
+
+/* dvs_msgs/Event {uint16 x; uint16 y; ros::Time ts; bool polarity} as roscpp lays it out
+ * (16 bytes).  Only x, y are read on the device; ts is read by the host packet stage. */
+typedef struct emvs_event {
+  uint16_t x, y;
+  uint32_t sec, nsec;
+  uint8_t polarity;
+  uint8_t pad_[3];
+} emvs_event;
+
+/* kindr::minimal::QuatTransformation: unit quaternion (w,x,y,z) + position, double. */
+typedef struct emvs_pose {
+  double q[4];
+  double t[3];
+} emvs_pose;
+
+/* One control pose of a LinearTrajectory (std::map<ros::Time, Transformation>, TRJ:11). */
+typedef struct emvs_stamped_pose {
+  uint32_t sec, nsec;
+  emvs_pose T;
+} emvs_stamped_pose;
+
+/* Output of the packet stage of evaluateDSI (MAP:88-126): the pixel homography H_z0_px
+ * (row-major) that maps a rectified event pixel onto plane Z0 of the reference view, the
+ * camera centre C in the reference view, and the index of the packet's first event. */
+typedef struct emvs_packet {
+  float H[9];
+  float C[3];
+  uint64_t first_event;
+} emvs_packet;
+
+/* EMVS::ShapeDSI (MHP:40-65) + the quantities MapperEMVS::setupDSI derives (MAP:208-241). */
+typedef struct emvs_shape {
+  uint32_t dimX, dimY, dimZ;   /* 0 for dimX/dimY -> sensor size (MAP:216-217)              */
+  float min_depth, max_depth;
+  float fov_deg;               /* < 10 -> use the camera's fx (MAP:220-224)                 */
+  int32_t inverse_depth;       /* 0: LinearDepthVector (build default), 1: InverseDepthVector */
+} emvs_shape;
+
+/* What the reference takes from image_geometry::PinholeCameraModel (MAP:34-48): full
+ * resolution and the PROJECTION-matrix intrinsics fx(), fy(), cx(), cy(). */
+typedef struct emvs_camera {
+  uint32_t width, height;
+  float fx, fy, cx, cy;
+} emvs_camera;
+
+/* Fusion ids as used by --stereo_fusion / --temporal_fusion (P1:136-158, docs/running.md). */
+enum {
+  EMVS_FUSE_MIN = 1, EMVS_FUSE_HM = 2, EMVS_FUSE_GM = 3,
+  EMVS_FUSE_AM = 4, EMVS_FUSE_RMS = 5, EMVS_FUSE_MAX = 6
+};
+
+/* Pairwise / in-place voxel ops of Grid3D (G3H:64-192). */
+enum {
+  EMVS_OP_ADD = 0,            /* addTwoGrids            G3H:64-70    a += b                 */
+  EMVS_OP_MIN = 1,            /* minTwoGrids            G3H:111-117                          */
+  EMVS_OP_HM = 2,             /* harmonicMeanTwoGrids   G3H:119-127  2ab/(a+b+eps)          */
+  EMVS_OP_GM = 3,             /* geometricMeanTwoGrids  G3H:150-156  sqrt(ab)               */
+  EMVS_OP_AM = 4,             /* arithmeticMeanTwoGrids G3H:158-164  0.5(a+b)               */
+  EMVS_OP_RMS = 5,            /* rmsTwoGrids            G3H:141-148  sqrt(0.5(a^2+b^2))     */
+  EMVS_OP_MAX = 6,            /* maxTwoGrids            G3H:186-192                          */
+  EMVS_OP_HM_N = 7,           /* harmonicMeanTwoGrids(g,n,eps) G3H:130-139                   */
+  EMVS_OP_ADD_INV = 8,        /* addInverseOfTwoGrids   G3H:72-78    a += 1/(eps+b)         */
+  EMVS_OP_HM_FROM_SUMINV = 9, /* computeHMfromSumOfInv  G3H:80-86    a = n/a   (b unused)   */
+  EMVS_OP_AM_FROM_SUM = 10    /* computeAMfromSum       G3H:87-93    a = a/n   (b unused)   */
+};
+
+/* emvs_mapper_build flags */
+enum {
+  EMVS_BUILD_RESET = 0,       /* dsi_.resetGrid() then vote (MAP:145-146) — the reference behaviour */
+  EMVS_BUILD_ACCUMULATE = 1   /* vote on top of the current contents (sub-interval sharding)  */
+};
+
+typedef struct emvs_context emvs_context;  /* one CUDA device + stream + scratch              */
+typedef struct emvs_grid emvs_grid;        /* a device-resident DSI volume    == Grid3D        */
+typedef struct emvs_mapper emvs_mapper;    /* camera + DSI shape + its grid   == MapperEMVS    */
+
+/* ---- library / context ---------------------------------------------------------------- */
+EMVS_API int emvs_abi_version(void);
+EMVS_API const char* emvs_last_error(void);
+
+/* Create a context on CUDA device `device`.  Fails (EMVS_ERR_CUDA) when no sm_10x device. */
+EMVS_API int emvs_context_create(int device, emvs_context** out);
+EMVS_API int emvs_context_destroy(emvs_context* ctx);
+EMVS_API int emvs_context_sync(emvs_context* ctx);
+/* Tuning: number of Z-planes voted per pass over the event list (0 = automatic). */
+EMVS_API int emvs_context_set_slab(emvs_context* ctx, uint32_t planes_per_slab);
+/* Number of kernels this library launched on the context so far (bench `gpu_launches`). */
+EMVS_API int emvs_context_launch_count(emvs_context* ctx, uint64_t* out);
+/* Per-launch device timing of the vote kernel (the dominant kernel; bench.py's roofline):
+ * enable -> every later vote launch is bracketed by a cudaEvent pair on the context's stream;
+ * emvs_context_vote_time syncs and returns the summed duration and the launch count since the
+ * last enable. */
+EMVS_API int emvs_context_profile_vote(emvs_context* ctx, int enable);
+EMVS_API int emvs_context_vote_time(emvs_context* ctx, double* total_ms, uint64_t* n_launches);
+/* The context's cudaStream_t, for callers that time with CUDA events. */
+EMVS_API int emvs_context_stream(emvs_context* ctx, void** out_stream);
+
+/* Device-side timing on the context's stream (cudaEvent pair). */
+typedef struct emvs_timer emvs_timer;
+EMVS_API int emvs_timer_create(emvs_context* ctx, emvs_timer** out);
+EMVS_API int emvs_timer_destroy(emvs_timer* t);
+EMVS_API int emvs_timer_start(emvs_timer* t);                   /* record the start event */
+EMVS_API int emvs_timer_stop(emvs_timer* t);                    /* record the stop event  */
+EMVS_API int emvs_timer_elapsed_ms(emvs_timer* t, float* ms);   /* waits for the stop event */
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+EMVS_API int emvs_host_alloc(size_t bytes, void** out);
+EMVS_API int emvs_host_free(void* p);
+
+/* ---- host-side geometry (no GPU needed) ------------------------------------------------- */
+
+/* raw_depths_vec_ = [cellIndexToDepth(i)]  (DV:88-103 / DV:131-148, MAP:213-214). */
+EMVS_API int emvs_depth_vector(const emvs_shape* shape, float* out_depths /* dimZ */);
+/* Virtual camera of the DSI (MAP:219-239): out = {fx, fy, cx, cy}. */
+EMVS_API int emvs_virtual_camera(const emvs_camera* cam, const emvs_shape* shape, float out[4]);
+/* LinearTrajectory::getPoseAt (TRJ:92-127).  *found = 0 when t is outside the control poses. */
+EMVS_API int emvs_trajectory_pose_at(const emvs_stamped_pose* traj, size_t n_poses, uint32_t sec, uint32_t nsec,
+                            emvs_pose* out, int* found);
+EMVS_API int emvs_pose_compose(const emvs_pose* a, const emvs_pose* b, emvs_pose* out); /* a * b */
+EMVS_API int emvs_pose_inverse(const emvs_pose* a, emvs_pose* out);
+/* Packet stage of evaluateDSI (MAP:86-126): groups events in packets of 1024, one pose per
+ * packet at the timestamp of its middle event, skipping one event on a pose miss.  Writes up
+ * to max_packets packets and the number produced to *n_packets.  Returns EMVS_ERR_TOO_FEW when
+ * n_events < 1024. */
+EMVS_API int emvs_packetize(const emvs_event* events, size_t n_events,
+                   const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w,
+                   const emvs_camera* cam, const float virt[4], float z0,
+                   emvs_packet* out, size_t max_packets, size_t* n_packets);
+
+/* ---- Grid3D ------------------------------------------------------------------------------ */
+EMVS_API int emvs_grid_create(emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ, emvs_grid** out); /* G3C:30-45 (zeroed) */
+EMVS_API int emvs_grid_destroy(emvs_grid* g);
+EMVS_API int emvs_grid_dims(const emvs_grid* g, uint32_t* dimX, uint32_t* dimY, uint32_t* dimZ);               /* G3H:230-235 */
+EMVS_API int emvs_grid_reset(emvs_grid* g);                                                                     /* G3C:67-70 */
+/* a = op(a, b[, n, eps]);  b may be NULL for the two finalisers.  (G3H:64-192) */
+EMVS_API int emvs_grid_op(emvs_grid* a, const emvs_grid* b, int op, int n, float eps);
+/* a = b (device copy) — the `resetGrid(); addTwoGrids(g)` initialisation idiom, P1:126-127. */
+EMVS_API int emvs_grid_copy(emvs_grid* dst, const emvs_grid* src);
+/* Host <-> device transfer of the whole volume, layout x + dimX*(y + dimY*z) (G3H:34-35). */
+EMVS_API int emvs_grid_download(const emvs_grid* g, float* host_out);
+EMVS_API int emvs_grid_upload(emvs_grid* g, const float* host_in);
+/* Grid3D::computeMeanSquare (G3C:164-174): sum(x^2)/N in double. */
+EMVS_API int emvs_grid_mean_square(const emvs_grid* g, double* out);
+/* Grid3D::collapseMaxZSlice (G3C:115-137) + convertDepthIndicesToValues (MAP:302-313).
+ * conf: dimY*dimX float; idx: dimY*dimX of uint8 when dimZ <= 256 (reference CV_8U) else
+ * uint16 (extension); depth (may be NULL, needs `depths`): depths[idx].  First maximum wins. */
+EMVS_API int emvs_grid_collapse_max(const emvs_grid* g, const float* depths, float* conf, void* idx, float* depth);
+/* Fast path of process_1 step 2+3 (P1:126-191, MAP:367-369): n-ary fusion of `n` grids with
+ * stereo-fusion id `method` (1..6) folded left-to-right exactly like the reference's pairwise
+ * calls (HM with n == 3 uses the HM_N step for the third grid, P1:176; GM/AM/RMS with n > 2 are
+ * n-ary extensions folded pairwise), then Z-argmax, without materialising the fused volume.
+ * If fused_out != NULL the fused volume is also written there. */
+EMVS_API int emvs_fuse_collapse(emvs_grid* const* grids, int n, int method, const float* depths,
+                       emvs_grid* fused_out, float* conf, void* idx, float* depth);
+/* Same sweep with DEVICE output pointers and a DEVICE depth table (emvs_mapper_depths_device);
+ * asynchronous on the context's stream: nothing is copied to the host (bench `value`). */
+EMVS_API int emvs_fuse_collapse_device(emvs_grid* const* grids, int n, int method, const float* d_depths,
+                              emvs_grid* fused_out, float* d_conf, void* d_idx, float* d_depth);
+/* Raw device pointer of the volume (for collectives run by the caller, e.g. torch.distributed). */
+EMVS_API int emvs_grid_device_ptr(const emvs_grid* g, void** out);
+
+/* ---- MapperEMVS ---------------------------------------------------------------------------- */
+/* MapperEMVS::MapperEMVS(cam, shape) (MAP:29-64): derives the depth table and the virtual
+ * camera, allocates the DSI.  The rectification LUT (MAP:256-299, built by OpenCV /
+ * image_geometry in the reference) is an INPUT: set it with emvs_mapper_set_lut. */
+EMVS_API int emvs_mapper_create(emvs_context* ctx, const emvs_camera* cam, const emvs_shape* shape, emvs_mapper** out);
+EMVS_API int emvs_mapper_destroy(emvs_mapper* m);
+/* precomputed_rectified_points_: interleaved (x,y) float pairs indexed y*width + x (MAP:275,296). */
+EMVS_API int emvs_mapper_set_lut(emvs_mapper* m, const float* lut_xy, size_t n_pixels);
+EMVS_API int emvs_mapper_shape(const emvs_mapper* m, emvs_shape* shape_out, float virt_out[4]);
+EMVS_API int emvs_mapper_depths(const emvs_mapper* m, float* out_depths /* dimZ */);
+EMVS_API int emvs_mapper_grid(emvs_mapper* m, emvs_grid** out);   /* the public member dsi_ (MHP:116)   */
+EMVS_API int emvs_mapper_depths_device(const emvs_mapper* m, const float** out_d_depths); /* device copy of the table */
+/* Event stage + resetGrid + fillVoxelGrid of evaluateDSI (MAP:129-205) for packets already
+ * computed by the packet stage.  events/packets are HOST pointers. */
+EMVS_API int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                      const emvs_packet* packets, size_t n_packets, int flags);
+/* Same with DEVICE-resident events/packets (bench `value`: inputs already in HBM). */
+EMVS_API int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_events,
+                             const void* d_packets, size_t n_packets, int flags);
+/* Whole MapperEMVS::evaluateDSI (MAP:67-148): packet stage on the host, the rest on the GPU.
+ * Returns EMVS_ERR_TOO_FEW (-> `false`) when n_events < 1024. */
+EMVS_API int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                             const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w);
+/* Build-defined integer observable: accepted (event, plane k) votes of the last
+ * build(s) since the last RESET, one uint64 per plane. */
+EMVS_API int emvs_mapper_counts(const emvs_mapper* m, uint64_t* per_plane /* dimZ */);
+
+/* ---- multi-GPU (one process per GPU) --------------------------------------------------------- */
+/* NCCL is resolved at run time (dlopen of the libnccl already loaded in the process, else
+ * libnccl.so.2).  Rank 0 calls emvs_comm_unique_id and ships the 128 bytes to the others. */
+EMVS_API int emvs_comm_unique_id(uint8_t out_id[128]);
+EMVS_API int emvs_comm_init(emvs_context* ctx, const uint8_t id[128], int n_ranks, int rank);
+EMVS_API int emvs_comm_destroy(emvs_context* ctx);
+/* In-place sum of a partial DSI over all ranks (ncclAllReduce float32 sum, chunked by Z-slab). */
+EMVS_API int emvs_grid_allreduce(emvs_grid* g);
+/* Same, enqueued on the context's stream without waiting for completion. */
+EMVS_API int emvs_grid_allreduce_async(emvs_grid* g);
+/* Sum of the per-plane vote counts over all ranks. */
+EMVS_API int emvs_mapper_counts_allreduce(emvs_mapper* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMVS_B200_H_ */
