@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--events-per-cam", type=int, default=5_000_000)
     ap.add_argument("--kind", default="structured", choices=["structured", "uniform"])
-    ap.add_argument("--cpu-sample-events", type=int, default=2_000_000,
+    ap.add_argument("--cpu-sample-events", type=int, default=5_000_000,
                     help="events per camera of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -6,6 +6,7 @@
 #include "emvs_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -50,6 +51,10 @@ using namespace emvs;
 // objects
 // ---------------------------------------------------------------------------------------------
 struct emvs_context {
+  // Grids, mappers and timers keep their context alive: emvs_context_destroy only drops the
+  // caller's reference, the teardown happens when the last dependent object is destroyed (so a
+  // garbage-collected binding may release objects in any order).
+  std::atomic<int> refs{1};
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
@@ -279,7 +284,8 @@ int collapse_to_host(emvs_context* ctx, const FuseArgs& A, uint32_t dimX, uint32
   REQUIRE(!depth || h_depths, EMVS_ERR_INVALID, "collapse: depth output needs the depth table");
   const uint32_t n_pix = dimX * dimY;
   const size_t idx_sz = dimZ <= 256 ? 1 : 2;
-  const size_t off_depth = (size_t)n_pix * 4, off_idx = (size_t)n_pix * 8, off_tab = (size_t)n_pix * 10 + 16;
+  const size_t off_depth = (size_t)n_pix * 4, off_idx = (size_t)n_pix * 8;
+  const size_t off_tab = ((size_t)n_pix * 10 + 15) & ~(size_t)15;
   const size_t total = off_tab + (size_t)dimZ * 4;
   int rc = grow(&ctx->d_out, &ctx->out_cap, total);
   if (rc) return rc;
@@ -287,7 +293,7 @@ int collapse_to_host(emvs_context* ctx, const FuseArgs& A, uint32_t dimX, uint32
   float* d_conf = (float*)base;
   float* d_depth = depth ? (float*)(base + off_depth) : nullptr;
   void* d_idx = base + off_idx;
-  float* d_tab = (float*)(base + ((off_tab + 15) & ~(size_t)15));
+  float* d_tab = (float*)(base + off_tab);
   cudaStream_t st = ctx->stream;
   if (depth) CUDA_TRY(cudaMemcpyAsync(d_tab, h_depths, (size_t)dimZ * 4, cudaMemcpyHostToDevice, st));
   rc = launch_fuse_collapse(ctx, A, n_pix, dimZ, d_tab, fused, d_conf, d_idx, (int)idx_sz, d_depth);
@@ -343,9 +349,20 @@ int emvs_context_create(int device, emvs_context** out)
   return EMVS_OK;
 }
 
+static void context_release(emvs_context* ctx);
+
 int emvs_context_destroy(emvs_context* ctx)
 {
   if (!ctx) return EMVS_OK;
+  context_release(ctx);
+  return EMVS_OK;
+}
+
+static void context_retain(emvs_context* ctx) { ctx->refs.fetch_add(1); }
+
+static void context_release(emvs_context* ctx)
+{
+  if (ctx->refs.fetch_sub(1) != 1) return;
   DeviceGuard guard(ctx->device);
   if (ctx->comm) emvs_comm_destroy(ctx);
   cudaStreamSynchronize(ctx->stream);
@@ -359,7 +376,6 @@ int emvs_context_destroy(emvs_context* ctx)
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
-  return EMVS_OK;
 }
 
 int emvs_context_sync(emvs_context* ctx)
@@ -427,6 +443,7 @@ int emvs_timer_create(emvs_context* ctx, emvs_timer** out)
   emvs_timer* t = new (std::nothrow) emvs_timer;
   REQUIRE(t, EMVS_ERR_INVALID, "out of host memory");
   t->ctx = ctx;
+  context_retain(ctx);
   CUDA_TRY(cudaEventCreate(&t->a));
   CUDA_TRY(cudaEventCreate(&t->b));
   *out = t;
@@ -438,6 +455,7 @@ int emvs_timer_destroy(emvs_timer* t)
   if (!t) return EMVS_OK;
   cudaEventDestroy(t->a);
   cudaEventDestroy(t->b);
+  context_release(t->ctx);
   delete t;
   return EMVS_OK;
 }
@@ -565,6 +583,7 @@ int emvs_grid_create(emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t d
     delete g;
     return EMVS_ERR_CUDA;
   }
+  context_retain(ctx);
   *out = g;
   return EMVS_OK;
 }
@@ -575,6 +594,7 @@ int emvs_grid_destroy(emvs_grid* g)
   DeviceGuard guard(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
   cudaFree(g->d);
+  context_release(g->ctx);
   delete g;
   return EMVS_OK;
 }
@@ -736,6 +756,7 @@ int emvs_mapper_create(emvs_context* ctx, const emvs_camera* cam, const emvs_sha
   emvs_mapper* m = new (std::nothrow) emvs_mapper;
   REQUIRE(m, EMVS_ERR_INVALID, "out of host memory");
   m->ctx = ctx;
+  context_retain(ctx);
   m->cam = *cam;
   m->shape = *shape;
   if (!m->shape.dimX) m->shape.dimX = cam->width;    // MAP:216
@@ -744,7 +765,7 @@ int emvs_mapper_create(emvs_context* ctx, const emvs_camera* cam, const emvs_sha
   m->depths.resize(shape->dimZ);
   host_depth_vector(m->shape, m->depths.data());
   rc = emvs_grid_create(ctx, m->shape.dimX, m->shape.dimY, m->shape.dimZ, &m->grid);
-  if (rc) { delete m; return rc; }
+  if (rc) { context_release(ctx); delete m; return rc; }
   cudaError_t e = cudaMalloc((void**)&m->d_depths, sizeof(float) * shape->dimZ);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_depths, m->depths.data(), sizeof(float) * shape->dimZ, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_lut, sizeof(float2) * (size_t)cam->width * cam->height);
@@ -769,6 +790,7 @@ int emvs_mapper_destroy(emvs_mapper* m)
   cudaFree(m->d_depths);
   cudaFree(m->d_lut);
   cudaFree(m->d_counts);
+  context_release(m->ctx);
   delete m;
   return EMVS_OK;
 }

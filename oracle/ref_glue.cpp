@@ -1,0 +1,83 @@
+// ref_glue.cpp — C entry points over the REFERENCE's own Grid3D (cartesian3dgrid.h / .cpp compiled
+// in place from /root/reference, never copied), used to pin the restated oracle and to generate
+// tests/golden/.  TEST INFRASTRUCTURE ONLY.  Only the cv::Mat container is a stand-in
+// (oracle/shim/emvs_cv_shim.h); every float operation executed here is the reference's.
+#include <cartesian3dgrid/cartesian3dgrid.h>
+#include <mapper_emvs_stereo/depth_vector.hpp>
+
+#include <cstdint>
+#include <cstring>
+
+namespace {
+void load(Grid3D& g, const float* src, size_t n) { std::memcpy(g.getPointerToSlice(0), src, n * sizeof(float)); }
+void store(Grid3D& g, float* dst, size_t n) { std::memcpy(dst, g.getPointerToSlice(0), n * sizeof(float)); }
+}  // namespace
+
+extern "C" {
+
+// Grid3D::accumulateGridValueAt(x_f, y_f, grid) for n points on slice k of a (dimX,dimY,dimZ) grid
+// whose contents are vol (in/out).  cartesian3dgrid.h:253-273
+void ref_vote(uint32_t dimX, uint32_t dimY, uint32_t dimZ, float* vol, uint32_t k, const float* x, const float* y, uint64_t n)
+{
+  Grid3D g(dimX, dimY, dimZ);
+  const size_t cells = (size_t)dimX * dimY * dimZ;
+  load(g, vol, cells);
+  float* slice = g.getPointerToSlice((int)k);
+  for (uint64_t i = 0; i < n; ++i) g.accumulateGridValueAt(x[i], y[i], slice);
+  store(g, vol, cells);
+}
+
+// Voxel-wise ops, ids as in include/emvs_b200.h EMVS_OP_*.  cartesian3dgrid.h:64-192
+void ref_grid_op(int op, uint32_t dimX, uint32_t dimY, uint32_t dimZ, float* a, const float* b, int n, float eps)
+{
+  Grid3D ga(dimX, dimY, dimZ), gb(dimX, dimY, dimZ);
+  const size_t cells = (size_t)dimX * dimY * dimZ;
+  load(ga, a, cells);
+  if (b) load(gb, b, cells);
+  switch (op) {
+    case 0: ga.addTwoGrids(gb); break;
+    case 1: ga.minTwoGrids(gb); break;
+    case 2: ga.harmonicMeanTwoGrids(gb, eps); break;
+    case 3: ga.geometricMeanTwoGrids(gb); break;
+    case 4: ga.arithmeticMeanTwoGrids(gb); break;
+    case 5: ga.rmsTwoGrids(gb); break;
+    case 6: ga.maxTwoGrids(gb); break;
+    case 7: ga.harmonicMeanTwoGrids(gb, n, eps); break;
+    case 8: ga.addInverseOfTwoGrids(gb, eps); break;
+    case 9: ga.computeHMfromSumOfInv(n); break;
+    case 10: ga.computeAMfromSum(n); break;
+    default: break;
+  }
+  store(ga, a, cells);
+}
+
+// Grid3D::collapseMaxZSlice.  cartesian3dgrid.cpp:115-137 (index is uchar: dimZ <= 256)
+void ref_collapse_max(uint32_t dimX, uint32_t dimY, uint32_t dimZ, const float* vol, float* conf, uint8_t* idx)
+{
+  Grid3D g(dimX, dimY, dimZ);
+  load(g, vol, (size_t)dimX * dimY * dimZ);
+  cv::Mat mv, mi;
+  g.collapseMaxZSlice(&mv, &mi);
+  std::memcpy(conf, mv.data(), (size_t)dimX * dimY * sizeof(float));
+  std::memcpy(idx, mi.data(), (size_t)dimX * dimY);
+}
+
+// raw_depths_vec_ as MapperEMVS::setupDSI builds it (mapper_emvs_stereo.cpp:213-214) from the
+// reference's own depth_vector.hpp: LinearDepthVector (:76-114) or InverseDepthVector (:119-163).
+void ref_depth_vector(int inverse, float zmin, float zmax, uint64_t nz, float* out)
+{
+  std::vector<float> v;
+  if (inverse) v = EMVS::InverseDepthVector(zmin, zmax, (size_t)nz).getDepthVector();
+  else v = EMVS::LinearDepthVector(zmin, zmax, (size_t)nz).getDepthVector();
+  std::memcpy(out, v.data(), v.size() * sizeof(float));
+}
+
+// Grid3D::computeMeanSquare.  cartesian3dgrid.cpp:164-174
+double ref_mean_square(uint32_t dimX, uint32_t dimY, uint32_t dimZ, const float* vol)
+{
+  Grid3D g(dimX, dimY, dimZ);
+  load(g, vol, (size_t)dimX * dimY * dimZ);
+  return g.computeMeanSquare();
+}
+
+}  // extern "C"

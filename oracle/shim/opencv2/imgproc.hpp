@@ -1,0 +1,1 @@
+#include "../emvs_cv_shim.h"

@@ -1,0 +1,76 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_check.py
+
+Every rank builds its packet sub-interval of every camera (dvs_mcemvs_b200.shard.plan), the partial
+DSIs are summed with the engine's ncclAllReduce, then fused + collapsed.  Rank 0 also builds the
+unsharded DSIs on its own GPU and checks: vote counts bit-exact, DSI / confidence within float-sum
+tolerance, argmax identical away from near-ties.  Exits non-zero on any mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from dvs_mcemvs_b200 import api, shard, synth  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = api.Context(local)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.comm_init(idt.cpu().numpy().tobytes(), world, rank)
+
+    for name, n_ev in (("esim_small", 50_000), ("dsec_stereo", 400_000)):
+        sc, _, method, _ = synth.config(name, events_per_cam=n_ev)
+        cams = sc.rig.cams
+        events = [sc.events(i, n_ev) for i in range(len(cams))]     # same seed on every rank: identical streams
+        trajs = [api.LinearTrajectory(sc.trajectory(i)) for i in range(len(cams))]
+        T = sc.T_rv_w()
+        mappers = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
+        packets = [m.packetize(ev, tr, T) for m, ev, tr in zip(mappers, events, trajs)]
+        for cam, lo, hi in shard.plan([len(p) for p in packets], world, rank):
+            mappers[cam].build(events[cam], packets[cam][lo:hi])
+            mappers[cam].dsi_.allreduce()
+            mappers[cam].counts_allreduce()
+        conf, idx, depth = api.fuse_collapse([m.dsi_ for m in mappers], method, mappers[0].raw_depths_vec_)
+        if rank == 0:
+            full = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
+            for m, ev, pk in zip(full, events, packets):
+                m.build(ev, pk)
+            for m, f in zip(mappers, full):
+                assert np.array_equal(m.counts(), f.counts()), "sharded vote counts differ from unsharded"
+                np.testing.assert_allclose(m.dsi_.download(), f.dsi_.download(), rtol=1e-5, atol=1e-5)
+            conf_f, idx_f, depth_f = api.fuse_collapse([m.dsi_ for m in full], method, full[0].raw_depths_vec_)
+            np.testing.assert_allclose(conf, conf_f, rtol=1e-4, atol=1e-6)
+            agree = float((idx == idx_f).mean())
+            assert agree > 0.999, agree
+            print(f"mgpu_check {name}: world={world} counts exact, conf within 1e-4, index agreement {agree:.5f}")
+        # all ranks hold identical maps after the allreduce (same summands, same NCCL reduction order)
+        t = torch.from_numpy(conf.copy()).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(t, ref), "ranks disagree on the confidence map"
+        for m in mappers:
+            m.close()
+    ctx.comm_destroy()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("mgpu_check ok")
+
+
+if __name__ == "__main__":
+    main()
