@@ -192,7 +192,7 @@ def run_reference(args):
     n_cams = 2
     value = n_cams * n_full / t / 1e6
     last["value"] = value
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -395,7 +395,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"], _ = cpu_reference(args, n_ev)
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         ctx.comm_destroy()
         dist.destroy_process_group()
@@ -410,7 +410,16 @@ def load_ncu_traffic():
     return None
 
 
+def _emit(line):
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 if __name__ == "__main__":
+    # Exactly ONE line may reach stdout (the driver parses it): route everything libraries print
+    # (NCCL banners, torchrun notices) to stderr and keep the real stdout for the JSON line.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -65,7 +65,15 @@ struct emvs_context {
   size_t quad_bytes = 0;
   // grow-only device staging
   void* d_events = nullptr;  size_t events_cap = 0;
-  void* d_packets = nullptr; size_t packets_cap = 0;
+  void* d_packets[2] = {nullptr, nullptr}; size_t packets_cap[2] = {0, 0};  // alternate per build (see build_from_host)
+  unsigned build_parity = 0;
+  // host->device staging runs on its own stream so that the upload of the next camera's events
+  // overlaps the vote kernels of the previous one
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied = nullptr;     // inputs of the current build are in HBM
+  cudaEvent_t ev_consumed = nullptr;   // k_warp_events of the last build has read d_events
+  bool consumed_recorded = false;
+  bool mark_consumed = false;          // build_on_device records ev_consumed after the event stage
   float2* d_xy0 = nullptr;   size_t xy0_cap = 0;
   void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
   double* d_partial = nullptr;                        // 1024 partial sums + 1 result
@@ -130,8 +138,9 @@ int grow(void** p, size_t* cap, size_t need)
 inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 // Planes voted per pass over the event list.  The quad scratch of a slab (4 copies) must stay
-// L2-resident together with the streaming event reads; 32 MiB is a conservative default for
-// the 126 MB L2 (tuned with tools/red_microbench).
+// L2-resident together with the streaming event reads.  Measured on B200 (126 MB L2) at
+// 640x480: 16 planes (79 MB) is the fastest, 32 planes (157 MB) falls off the L2 cliff
+// (profiles/r1_slab_sweep.md); 80 MiB is the budget.
 uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ)
 {
   uint32_t s = ctx->slab_override;
@@ -140,7 +149,7 @@ uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint
   }
   if (!s) {
     const size_t plane_bytes = (size_t)ceil_div(dimX, 2) * ceil_div(dimY, 2) * 64;
-    const size_t budget = (size_t)32 << 20;
+    const size_t budget = (size_t)80 << 20;
     s = (uint32_t)std::max<size_t>(1, budget / std::max<size_t>(plane_bytes, 1));
   }
   s = std::min(s, dimZ);
@@ -195,6 +204,10 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
     k_warp_events<<<blocks, 256, 0, st>>>(d_ev, d_pk, m->d_lut, m->cam.width, m->cam.height, ctx->d_xy0,
                                           (unsigned long long)n_voted);
     ctx->launches++;
+    if (ctx->mark_consumed) {
+      CUDA_TRY(cudaEventRecord(ctx->ev_consumed, st));
+      ctx->consumed_recorded = true;
+    }
   }
 
   VoteParams P;
@@ -339,6 +352,9 @@ int emvs_context_create(int device, emvs_context** out)
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_partial, sizeof(double) * 1025);
   if (e != cudaSuccess) {
     set_error("context_create: %s", cudaGetErrorString(e));
@@ -367,8 +383,13 @@ static void context_release(emvs_context* ctx)
   if (ctx->comm) emvs_comm_destroy(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->quad);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   cudaFree(ctx->d_events);
-  cudaFree(ctx->d_packets);
+  cudaFree(ctx->d_packets[0]);
+  cudaFree(ctx->d_packets[1]);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->ev_consumed) cudaEventDestroy(ctx->ev_consumed);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_xy0);
   cudaFree(ctx->d_out);
   cudaFree(ctx->d_partial);
@@ -846,6 +867,46 @@ static int check_packets(const emvs_packet* pk, size_t n_packets, size_t n_event
   return EMVS_OK;
 }
 
+// Host-buffer build.  Staging protocol (one context = one in-order pipeline):
+//   copy_stream:  wait(ev_consumed of the previous build) -> H2D events, packets -> record ev_copied
+//   stream:       wait(ev_copied) -> k_warp_events -> record ev_consumed -> slab loop
+//   host:         waits for ev_copied only, so the caller may reuse its buffers and issue the next
+//                 camera's build, whose upload then overlaps this build's vote kernels.
+// d_events is read by k_warp_events only; d_packets is read by every vote launch, hence two
+// alternating packet buffers: build N+2 can only upload after k_warp_events of build N+1 ran,
+// which is stream-ordered behind the last vote of build N.
+static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
+                           size_t n_packets, int flags)
+{
+  emvs_context* ctx = m->ctx;
+  const unsigned par = ctx->build_parity++ & 1u;
+  if (n_packets) {
+    size_t lo = n_events, last = 0;   // only the span of events that packets reference has to travel
+    for (size_t j = 0; j < n_packets; ++j) {
+      lo = std::min<size_t>(lo, packets[j].first_event);
+      last = std::max<size_t>(last, packets[j].first_event + EMVS_PACKET_SIZE);
+    }
+    int rc = grow(&ctx->d_events, &ctx->events_cap, n_events * sizeof(emvs_event));
+    if (rc) return rc;
+    rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par], n_packets * sizeof(emvs_packet));
+    if (rc) return rc;
+    if (ctx->consumed_recorded) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed, 0));
+    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + lo, events + lo, (last - lo) * sizeof(emvs_event),
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], packets, n_packets * sizeof(emvs_packet), cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+  }
+  ctx->mark_consumed = true;
+  const int rc = build_on_device(m, (const emvs_event*)ctx->d_events, n_events, (const emvs_packet*)ctx->d_packets[par],
+                                 n_packets, flags);
+  ctx->mark_consumed = false;
+  if (rc) return rc;
+  if (n_packets) CUDA_TRY(cudaEventSynchronize(ctx->ev_copied));
+  return EMVS_OK;
+}
+
 int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
                       size_t n_packets, int flags)
 {
@@ -854,28 +915,8 @@ int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events,
   REQUIRE(n_packets == 0 || (events && packets), EMVS_ERR_INVALID, "mapper_build: NULL events/packets");
   int rc = check_packets(packets, n_packets, n_events);
   if (rc) return rc;
-  emvs_context* ctx = m->ctx;
-  DeviceGuard guard(ctx->device);
-  if (n_packets) {
-    // Only the span of events that packets reference has to travel.
-    size_t last = 0;
-    for (size_t j = 0; j < n_packets; ++j) last = std::max<size_t>(last, packets[j].first_event + EMVS_PACKET_SIZE);
-    rc = grow(&ctx->d_events, &ctx->events_cap, n_events * sizeof(emvs_event));
-    if (rc) return rc;
-    rc = grow(&ctx->d_packets, &ctx->packets_cap, n_packets * sizeof(emvs_packet));
-    if (rc) return rc;
-    size_t lo = n_events;
-    for (size_t j = 0; j < n_packets; ++j) lo = std::min<size_t>(lo, packets[j].first_event);
-    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + lo, events + lo, (last - lo) * sizeof(emvs_event),
-                             cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_packets, packets, n_packets * sizeof(emvs_packet), cudaMemcpyHostToDevice,
-                             ctx->stream));
-  }
-  rc = build_on_device(m, (const emvs_event*)ctx->d_events, n_events, (const emvs_packet*)ctx->d_packets, n_packets,
-                       flags);
-  if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return EMVS_OK;
+  DeviceGuard guard(m->ctx->device);
+  return build_from_host(m, events, n_events, packets, n_packets, flags);
 }
 
 int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_events, const void* d_packets,

@@ -1,0 +1,85 @@
+// example_process1.cpp — a caller written against the reference's class API (MapperEMVS, Grid3D,
+// LinearTrajectory, process_1) running on the B200 engine: ESIM-like stereo rig, synthetic events
+// of a fronto-parallel plane at 2.5 m seen from a translating camera (SURVEY.md §4 known-answer
+// test: the argmax of every voted pixel must be the plane that contains 2.5 m).
+//   make -C dvs_mcemvs_b200/host && dvs_mcemvs_b200/host/example_process1
+#include "mapper_emvs_stereo/process1.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+int main()
+{
+  const uint32_t W = 240, H = 180;
+  const float f = 200.f, cx = 120.f, cy = 90.f, baseline = 0.2f, Zstar = 2.5f;
+  geometry_utils::CameraInfo cam;
+  cam.width = W; cam.height = H; cam.fx = cam.fy = f; cam.cx = cx; cam.cy = cy;
+  EMVS::ShapeDSI shape(0, 0, 64, 1.0f, 5.0f, 0.0f);
+  try {
+    EMVS::MapperEMVS mapper_fused(cam, shape), mapper0(cam, shape), mapper1(cam, shape);
+    mapper_fused.name = "fused"; mapper0.name = "0"; mapper1.name = "1";
+
+    // trajectory: camera 0 translates 0.2 m along x in 0.2 s; camera 1 sits `baseline` to its right
+    LinearTrajectory::PoseMap poses0, poses1;
+    const double q[4] = {1, 0, 0, 0};
+    for (int i = 0; i <= 10; ++i) {
+      const double t = 1000.0 + 0.02 * i - 0.01, x = 1.0 * (0.02 * i - 0.01);
+      const double p0[3] = {x, 0, 0}, p1[3] = {x + baseline, 0, 0};
+      poses0[geometry_utils::Time(t)] = geometry_utils::Transformation(q, p0);
+      poses1[geometry_utils::Time(t)] = geometry_utils::Transformation(q, p1);
+    }
+    LinearTrajectory traj0(poses0), traj1(poses1);
+    geometry_utils::Transformation T_w_rv;
+    traj0.getPoseAt(geometry_utils::Time(1000.09), T_w_rv);
+    const geometry_utils::Transformation T_rv_w = T_w_rv.inverse();
+
+    // events: random points on the plane Z = Zstar (world frame == camera-0 frame at x = 0)
+    std::mt19937 rng(1);
+    std::uniform_real_distribution<float> ux(-1.2f, 1.6f), uy(-0.9f, 0.9f);
+    std::vector<emvs_event> ev[2];
+    const size_t n_ev = 50000;
+    for (int c = 0; c < 2; ++c)
+      for (size_t i = 0; i < n_ev; ++i) {
+        const double t = 1000.0 + 0.18 * (double)i / n_ev;
+        const double camx = 1.0 * (t - 1000.0) + (c ? baseline : 0.0);
+        for (;;) {
+          const float X = ux(rng), Y = uy(rng);
+          const float u = f * (X - (float)camx) / Zstar + cx, v = f * Y / Zstar + cy;
+          const long xi = std::lround(u), yi = std::lround(v);
+          if (xi < 0 || yi < 0 || xi >= (long)W || yi >= (long)H) continue;
+          emvs_event e{};
+          e.x = (uint16_t)xi; e.y = (uint16_t)yi;
+          e.sec = (uint32_t)t; e.nsec = (uint32_t)((t - (uint32_t)t) * 1e9);
+          ev[c].push_back(e);
+          break;
+        }
+      }
+
+    emvs_host::Image<float> depth, conf;
+    emvs_host::Image<uint8_t> idx;
+    Process1Timing tm;
+    if (!process_1(mapper_fused, mapper0, mapper1, nullptr, ev[0], ev[1], nullptr, traj0, traj1, nullptr, T_rv_w,
+                   /*stereo_fusion=*/2, depth, conf, idx, true, &tm))
+      return 2;
+    std::printf("Mean square = %g (fused), %g (cam0)\n", mapper_fused.dsi_.computeMeanSquare(), mapper0.dsi_.computeMeanSquare());
+    std::printf("evaluateDSI: %.2f ms + %.2f ms (%.1f Mev/s), fusion+argmax %.2f ms\n", tm.build_ms[0], tm.build_ms[1],
+                2.0 * n_ev / (1e3 * (tm.build_ms[0] + tm.build_ms[1])), tm.fuse_ms);
+    // known answer: confident pixels sit on the plane containing Z*
+    const std::vector<float>& z = mapper0.depths();
+    size_t good = 0, total = 0;
+    for (int y = 10; y < (int)H - 10; ++y)
+      for (int x = 10; x < (int)W - 10; ++x)
+        if (conf.at(y, x) > 20.f) {
+          ++total;
+          if (std::fabs(z[idx.at(y, x)] - Zstar) <= (5.0f - 1.0f) / 64 + 1e-4f) ++good;
+        }
+    std::printf("confident pixels: %zu, on the Z* = %.2f m plane (+-1 cell): %zu\n", total, Zstar, good);
+    const bool ok = total > 1000 && good >= total * 99 / 100;
+    std::printf(ok ? "example_process1 ok\n" : "example_process1 FAILED\n");
+    return ok ? 0 : 1;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 3;
+  }
+}

@@ -21,7 +21,12 @@
  * otherwise.  Calls on one context are serialised by the caller (the reference's evaluateDSI
  * is not re-entrant either, MAP:79,83); different contexts may be driven from different
  * threads.  Unless a function says otherwise, pointer arguments are HOST pointers that are
- * only borrowed for the duration of the call, and the call returns after the work is complete.
+ * only borrowed for the duration of the call.  Execution model: every context is one in-order
+ * pipeline (a CUDA stream).  Calls that only produce DEVICE state (build, evaluate_dsi, grid ops,
+ * reset, copy, allreduce_async) return as soon as their host inputs have been consumed; calls
+ * that produce HOST output (download, collapse, counts, mean_square, timers) return after the
+ * output is complete, which implies everything issued before them.  emvs_context_sync waits
+ * for the whole pipeline (use it before reading a wall clock).
  */
 #ifndef EMVS_B200_H_
 #define EMVS_B200_H_
@@ -229,7 +234,9 @@ EMVS_API int emvs_mapper_depths(const emvs_mapper* m, float* out_depths /* dimZ 
 EMVS_API int emvs_mapper_grid(emvs_mapper* m, emvs_grid** out);   /* the public member dsi_ (MHP:116)   */
 EMVS_API int emvs_mapper_depths_device(const emvs_mapper* m, const float** out_d_depths); /* device copy of the table */
 /* Event stage + resetGrid + fillVoxelGrid of evaluateDSI (MAP:129-205) for packets already
- * computed by the packet stage.  events/packets are HOST pointers. */
+ * computed by the packet stage.  events/packets are HOST pointers (pinned memory uploads at full
+ * PCIe rate); the call returns once they are uploaded, so the upload of the next camera's events
+ * overlaps this camera's vote kernels. */
 EMVS_API int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events,
                       const emvs_packet* packets, size_t n_packets, int flags);
 /* Same with DEVICE-resident events/packets (bench `value`: inputs already in HBM). */
