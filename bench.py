@@ -20,8 +20,9 @@ milliseconds (fuse + argmax) and the build-only Mevents/s are reported beside it
          the events, build, fuse/argmax, D2H of depth/confidence/index all inside the timed region.
 
 Multi-GPU (weak scaling): every rank owns one packet-aligned sub-interval of EVERY camera's event
-stream (5 M events/camera/rank), builds partial DSIs, one ncclAllReduce(sum) per camera, then
-every rank fuses + collapses (replicated).  Launched by torchrun; torch.distributed is only the
+stream (5 M events/camera/rank), builds partial DSIs; each Z-slab is summed over the ranks with
+ncclAllReduce as soon as it is voted (overlapped with the next slab's votes), then every rank
+fuses + collapses (replicated).  Launched by torchrun; torch.distributed is only the
 rendezvous / barrier plumbing.
 
 `--impl reference` times the CPU oracle (the restated reference loops, oracle/) on a bounded
@@ -261,10 +262,7 @@ def run_b200(args):
 
     def step_device():
         for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
-            m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk))
-        if world > 1:
-            for m in mappers:
-                m.dsi_.allreduce_async()
+            m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1)
         collapse_device()
 
     t_all, t_build, t_depth = ctx.timer(), ctx.timer(), ctx.timer()
@@ -320,11 +318,10 @@ def run_b200(args):
 
         def step_host():
             for m, ev, tr in zip(mappers, h_events, ltrajs):
-                ok = m.evaluateDSI(ev, tr, T_rv_w)
-                assert ok
-            if world > 1:
-                for m in mappers:
-                    m.dsi_.allreduce()
+                if world > 1:   # sharded: host packet stage, then this rank's build with slab-wise allreduce
+                    m.build(ev, m.packetize(ev, tr, T_rv_w), allreduce=True)
+                else:
+                    assert m.evaluateDSI(ev, tr, T_rv_w)
             return api.fuse_collapse([m.dsi_ for m in mappers], method, depths)
 
         for _ in range(max(1, min(args.warmup, 2))):
@@ -387,7 +384,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "description": desc, "events_per_camera_per_gpu": n_ev, "cameras": n_cams,
                        "dsi": [dimX, dimY, dimZ], "fusion": "harmonic", "event_distribution": args.kind,
-                       "sharding": "event sub-interval per GPU, ncclAllReduce(sum) per camera DSI" if world > 1 else "none",
+                       "sharding": "event sub-interval per GPU; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting" if world > 1 else "none",
                        "l2": "inputs+DSIs (>700 MB/step) exceed the 126 MB L2; no explicit flush"},
             "build_mevents_per_s": n_cams * n_ev / (build_ms * 1e-3) / 1e6, "build_ms": build_ms,
             "depth_map_ms": depth_ms, "accepted_votes_per_step": votes,

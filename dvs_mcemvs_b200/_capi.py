@@ -20,7 +20,7 @@ PACKET_SIZE = 1024
 FUSE_MIN, FUSE_HM, FUSE_GM, FUSE_AM, FUSE_RMS, FUSE_MAX = 1, 2, 3, 4, 5, 6
 (OP_ADD, OP_MIN, OP_HM, OP_GM, OP_AM, OP_RMS, OP_MAX, OP_HM_N, OP_ADD_INV, OP_HM_FROM_SUMINV,
  OP_AM_FROM_SUM) = range(11)
-BUILD_RESET, BUILD_ACCUMULATE = 0, 1
+BUILD_RESET, BUILD_ACCUMULATE, BUILD_ALLREDUCE = 0, 1, 2
 
 # numpy views of the POD structs (layouts asserted against the C side in tests/test_abi.py)
 EVENT_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("sec", "<u4"), ("nsec", "<u4"),

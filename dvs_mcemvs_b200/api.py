@@ -365,18 +365,22 @@ class MapperEMVS:
         check(rc)
         return True
 
-    def build(self, events, packets, accumulate=False):
-        """Event stage + reset + fillVoxelGrid (mapper_emvs_stereo.cpp:129-205) for given packets."""
+    @staticmethod
+    def _flags(accumulate, allreduce):
+        return (capi.BUILD_ACCUMULATE if accumulate else capi.BUILD_RESET) | (capi.BUILD_ALLREDUCE if allreduce else 0)
+
+    def build(self, events, packets, accumulate=False, allreduce=False):
+        """Event stage + reset + fillVoxelGrid (mapper_emvs_stereo.cpp:129-205) for given packets.
+        allreduce=True: this is one rank's shard; Z-slabs are summed over the ranks while voting goes on."""
         events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
         packets = np.ascontiguousarray(packets, dtype=PACKET_DTYPE)
         check(_lib().emvs_mapper_build(self._h, ptr(events), events.shape[0], ptr(packets), packets.shape[0],
-                                       capi.BUILD_ACCUMULATE if accumulate else capi.BUILD_RESET))
+                                       self._flags(accumulate, allreduce)))
 
-    def build_device(self, d_events, n_events, d_packets, n_packets, accumulate=False):
+    def build_device(self, d_events, n_events, d_packets, n_packets, accumulate=False, allreduce=False):
         """Same with device pointers (ints); asynchronous on the context's stream."""
         check(_lib().emvs_mapper_build_device(self._h, C.c_void_p(d_events), int(n_events), C.c_void_p(d_packets),
-                                              int(n_packets),
-                                              capi.BUILD_ACCUMULATE if accumulate else capi.BUILD_RESET))
+                                              int(n_packets), self._flags(accumulate, allreduce)))
 
     def depths_device_ptr(self):
         p = C.c_void_p()

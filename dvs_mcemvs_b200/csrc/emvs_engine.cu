@@ -82,6 +82,9 @@ struct emvs_context {
   // NCCL
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;      // slab allreduces run here, overlapped with the next slab's votes
+  std::vector<cudaEvent_t> slab_events;    // slab s merged -> its allreduce may start
+  cudaEvent_t ev_comm_done = nullptr;
   // optional per-launch timing of the vote kernel (bench roofline): event pairs on `stream`
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop), prof_used of them recorded
@@ -169,19 +172,45 @@ int ensure_quad(emvs_context* ctx, size_t bytes)
   return EMVS_OK;
 }
 
-// Device part of evaluateDSI: event stage, (reset), slab loop of {vote, merge, re-zero}.
+int ncclAllReduce_checked(const NcclApi* api, emvs_context* ctx, float* p, size_t count, cudaStream_t st)
+{
+  const int r = api->AllReduce(p, p, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ctx->comm, (void*)st);
+  if (r != 0) set_error("ncclAllReduce(float32, sum) failed: %s", api->GetErrorString(r));
+  return r;
+}
+
+int ncclAllReduceU64_checked(const NcclApi* api, emvs_context* ctx, unsigned long long* p, size_t count, cudaStream_t st)
+{
+  const int r = api->AllReduce(p, p, count, /*ncclUint64*/ 5, /*ncclSum*/ 0, ctx->comm, (void*)st);
+  if (r != 0) set_error("ncclAllReduce(uint64, sum) failed: %s", api->GetErrorString(r));
+  return r;
+}
+
+// Device part of evaluateDSI: event stage, (reset), slab loop of {vote, merge, re-zero[, allreduce]}.
 int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, const emvs_packet* d_pk,
                     size_t n_packets, int flags)
 {
   emvs_context* ctx = m->ctx;
   emvs_grid* g = m->grid;
   const bool accumulate = (flags & EMVS_BUILD_ACCUMULATE) != 0;
+  const bool reduce = (flags & EMVS_BUILD_ALLREDUCE) != 0;
   cudaStream_t st = ctx->stream;
+  const NcclApi* nccl = nullptr;
+  if (reduce) {
+    REQUIRE(!accumulate, EMVS_ERR_INVALID, "build: EMVS_BUILD_ALLREDUCE cannot be combined with EMVS_BUILD_ACCUMULATE");
+    REQUIRE(ctx->comm, EMVS_ERR_STATE, "build: EMVS_BUILD_ALLREDUCE needs emvs_comm_init");
+    nccl = nccl_api();
+    if (!nccl) return EMVS_ERR_NCCL;
+  }
   if (!accumulate) {
     CUDA_TRY(cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned long long) * g->dimZ, st));
   }
   if (n_packets == 0) {
     if (!accumulate) CUDA_TRY(cudaMemsetAsync(g->d, 0, g->n_cells * sizeof(float), st));
+    if (reduce) {  // this rank has no packets but must still take part in the collective
+      if (ncclAllReduce_checked(nccl, ctx, g->d, g->n_cells, st)) return EMVS_ERR_NCCL;
+      if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, g->dimZ, st)) return EMVS_ERR_NCCL;
+    }
     return EMVS_OK;
   }
   (void)n_events;
@@ -243,6 +272,26 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
                                      accumulate ? 1 : 0);
     ctx->launches++;
     CUDA_TRY(cudaMemsetAsync(ctx->quad, 0, (size_t)nk * QW * QH * 4 * sizeof(float4), st));
+    if (reduce) {
+      // planes [k0, k0+nk) are final on this rank: sum them over the ranks on the communication
+      // stream while the next slab is being voted
+      const size_t si = k0 / slab;
+      while (ctx->slab_events.size() <= si) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->slab_events.push_back(e);
+      }
+      CUDA_TRY(cudaEventRecord(ctx->slab_events[si], st));
+      CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->slab_events[si], 0));
+      if (ncclAllReduce_checked(nccl, ctx, g->d + (size_t)k0 * dimX * dimY, (size_t)nk * dimX * dimY, ctx->comm_stream))
+        return EMVS_ERR_NCCL;
+    }
+  }
+  if (reduce) {
+    // the vote counters are final once the last vote kernel ran (recorded by the last slab event)
+    if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, dimZ, ctx->comm_stream)) return EMVS_ERR_NCCL;
+    CUDA_TRY(cudaEventRecord(ctx->ev_comm_done, ctx->comm_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_comm_done, 0));
   }
   CUDA_TRY(cudaGetLastError());
   return EMVS_OK;
@@ -387,6 +436,9 @@ static void context_release(emvs_context* ctx)
   cudaFree(ctx->d_events);
   cudaFree(ctx->d_packets[0]);
   cudaFree(ctx->d_packets[1]);
+  for (cudaEvent_t e : ctx->slab_events) cudaEventDestroy(e);
+  if (ctx->ev_comm_done) cudaEventDestroy(ctx->ev_comm_done);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->ev_consumed) cudaEventDestroy(ctx->ev_consumed);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -995,6 +1047,8 @@ int emvs_comm_init(emvs_context* ctx, const uint8_t id_bytes[128], int n_ranks, 
   NcclId id;
   memcpy(id.b, id_bytes, 128);
   NCCL_TRY(api, api->CommInitRank(&ctx->comm, n_ranks, id, rank));
+  if (!ctx->comm_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  if (!ctx->ev_comm_done) CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_comm_done, cudaEventDisableTiming));
   ctx->n_ranks = n_ranks;
   ctx->rank = rank;
   return EMVS_OK;
@@ -1008,6 +1062,7 @@ int emvs_comm_destroy(emvs_context* ctx)
   if (!api) return EMVS_ERR_NCCL;
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
   api->CommDestroy(ctx->comm);
   ctx->comm = nullptr;
   ctx->n_ranks = 1;

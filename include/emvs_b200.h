@@ -129,7 +129,11 @@ enum {
 /* emvs_mapper_build flags */
 enum {
   EMVS_BUILD_RESET = 0,       /* dsi_.resetGrid() then vote (MAP:145-146) — the reference behaviour */
-  EMVS_BUILD_ACCUMULATE = 1   /* vote on top of the current contents (sub-interval sharding)  */
+  EMVS_BUILD_ACCUMULATE = 1,  /* vote on top of the current contents (sub-interval sharding)  */
+  EMVS_BUILD_ALLREDUCE = 2    /* multi-GPU: this build is one rank's shard; every Z-slab is summed over
+                                 the ranks (ncclAllReduce) as soon as it is voted, overlapped with the
+                                 votes of the next slab; the vote counts are summed too.  Needs
+                                 emvs_comm_init; every rank must issue the same sequence of builds.      */
 };
 
 typedef struct emvs_context emvs_context;  /* one CUDA device + stream + scratch              */

@@ -33,7 +33,8 @@ def main():
     dist.broadcast(idt, 0)
     ctx.comm_init(idt.cpu().numpy().tobytes(), world, rank)
 
-    for name, n_ev in (("esim_small", 50_000), ("dsec_stereo", 400_000)):
+    for name, n_ev, overlapped in (("esim_small", 50_000, False), ("esim_small", 50_000, True),
+                                   ("dsec_stereo", 400_000, True)):
         sc, _, method, _ = synth.config(name, events_per_cam=n_ev)
         cams = sc.rig.cams
         events = [sc.events(i, n_ev) for i in range(len(cams))]     # same seed on every rank: identical streams
@@ -42,9 +43,12 @@ def main():
         mappers = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
         packets = [m.packetize(ev, tr, T) for m, ev, tr in zip(mappers, events, trajs)]
         for cam, lo, hi in shard.plan([len(p) for p in packets], world, rank):
-            mappers[cam].build(events[cam], packets[cam][lo:hi])
-            mappers[cam].dsi_.allreduce()
-            mappers[cam].counts_allreduce()
+            if overlapped:   # EMVS_BUILD_ALLREDUCE: every Z-slab is summed while the next one is voted
+                mappers[cam].build(events[cam], packets[cam][lo:hi], allreduce=True)
+            else:            # build, then one allreduce of the whole DSI
+                mappers[cam].build(events[cam], packets[cam][lo:hi])
+                mappers[cam].dsi_.allreduce()
+                mappers[cam].counts_allreduce()
         conf, idx, depth = api.fuse_collapse([m.dsi_ for m in mappers], method, mappers[0].raw_depths_vec_)
         if rank == 0:
             full = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
@@ -57,7 +61,7 @@ def main():
             np.testing.assert_allclose(conf, conf_f, rtol=1e-4, atol=1e-6)
             agree = float((idx == idx_f).mean())
             assert agree > 0.999, agree
-            print(f"mgpu_check {name}: world={world} counts exact, conf within 1e-4, index agreement {agree:.5f}")
+            print(f"mgpu_check {name} overlapped={overlapped}: world={world} counts exact, conf within 1e-4, index agreement {agree:.5f}")
         # all ranks hold identical maps after the allreduce (same summands, same NCCL reduction order)
         t = torch.from_numpy(conf.copy()).cuda()
         ref = t.clone()
