@@ -303,10 +303,22 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
 {
   const unsigned blocks = (n_pix + 127) / 128;
   cudaStream_t st = ctx->stream;
-#define LAUNCH(N) \
-  k_fuse_collapse<METHOD, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth)
+  // 16-byte path: plane size a multiple of 4 voxels and every pointer 16-byte aligned
+  bool vec = (n_pix % 4u) == 0 && dimZ >= (uint32_t)kFcZGroups;
+  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  for (int i = 0; i < A.n; ++i) vec = vec && aligned16(A.g[i]);
+  vec = vec && aligned16(fused) && aligned16(conf) && aligned16(depth) && (reinterpret_cast<uintptr_t>(idx) & 7u) == 0;
+  const unsigned vblocks = (n_pix / 4 + 31) / 32;
+#define LAUNCH(N)                                                                                                      \
+  do {                                                                                                                 \
+    if (vec) k_fuse_collapse_v4<METHOD, N><<<vblocks, 32 * kFcZGroups, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
+    else k_fuse_collapse<METHOD, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth);  \
+  } while (0)
   switch (A.n) {
-    case 1: k_fuse_collapse<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); break;
+    case 1:
+      if (vec) k_fuse_collapse_v4<EMVS_FUSE_MAX, 1><<<vblocks, 32 * kFcZGroups, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth);
+      else k_fuse_collapse<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth);
+      break;
     case 2: LAUNCH(2); break;
     case 3: LAUNCH(3); break;
     case 4: LAUNCH(4); break;
