@@ -303,22 +303,24 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
 {
   const unsigned blocks = (n_pix + 127) / 128;
   cudaStream_t st = ctx->stream;
-  // 16-byte path: plane size a multiple of 4 voxels and every pointer 16-byte aligned
-  bool vec = (n_pix % 4u) == 0 && dimZ >= (uint32_t)kFcZGroups;
+  // 16-byte path: plane size a multiple of 4 voxels and every pointer 16-byte aligned.
+  // EMVS_FC_ZGROUPS (tuning): 0 = scalar kernel, 1/2/4 = Z-groups of the vectorised kernel.
+  static const int zg_env = [] { const char* e = getenv("EMVS_FC_ZGROUPS"); return e ? atoi(e) : 4; }();
+  bool vec = zg_env > 0 && (n_pix % 4u) == 0 && dimZ >= 4u;
   auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   for (int i = 0; i < A.n; ++i) vec = vec && aligned16(A.g[i]);
   vec = vec && aligned16(fused) && aligned16(conf) && aligned16(depth) && (reinterpret_cast<uintptr_t>(idx) & 7u) == 0;
   const unsigned vblocks = (n_pix / 4 + 31) / 32;
-#define LAUNCH(N)                                                                                                      \
+#define LAUNCH_V(M, N)                                                                                                  \
   do {                                                                                                                 \
-    if (vec) k_fuse_collapse_v4<METHOD, N><<<vblocks, 32 * kFcZGroups, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
-    else k_fuse_collapse<METHOD, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth);  \
+    if (!vec) k_fuse_collapse<M, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
+    else if (zg_env == 1) k_fuse_collapse_v4<M, N, 1><<<vblocks, 32, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
+    else if (zg_env == 2) k_fuse_collapse_v4<M, N, 2><<<vblocks, 64, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
+    else k_fuse_collapse_v4<M, N, 4><<<vblocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
   } while (0)
+#define LAUNCH(N) LAUNCH_V(METHOD, N)
   switch (A.n) {
-    case 1:
-      if (vec) k_fuse_collapse_v4<EMVS_FUSE_MAX, 1><<<vblocks, 32 * kFcZGroups, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth);
-      else k_fuse_collapse<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth);
-      break;
+    case 1: LAUNCH_V(EMVS_FUSE_MAX, 1); break;
     case 2: LAUNCH(2); break;
     case 3: LAUNCH(3); break;
     case 4: LAUNCH(4); break;
@@ -329,6 +331,7 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
     default: set_error("fuse_collapse: need 1..8 grids"); return EMVS_ERR_INVALID;
   }
 #undef LAUNCH
+#undef LAUNCH_V
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return EMVS_OK;
