@@ -424,3 +424,80 @@ def test_full_size_properties(ctx, O):
     conf, idx = m.dsi_.collapseMaxZSlice()
     assert conf.max() > 1.0 and idx.dtype == np.uint8
     m.close()
+
+
+def _oracle_planes(O, case, cam_idx, planes):
+    """Oracle DSI of selected planes only (per-plane work is independent; depths[0] defines z0)."""
+    c = case.cams[cam_idx]
+    out = {}
+    for k in planes:
+        sel = np.array([case.depths[0], case.depths[k]], np.float32)
+        dsi_o, inb_o = O.build_dsi(case.events[cam_idx], case.packets[cam_idx], c.lut, c.width, sel, case.virts[cam_idx],
+                                   case.dimX, case.dimY)
+        out[k] = (dsi_o[1], int(inb_o[1]))
+    return out
+
+
+def test_config3_four_camera_geometric_mean(ctx, O):
+    """BASELINE.json configs[2] at reduced event count: 4-camera bar, 640x480x256, n-ary GM (extension
+    whose n = 2 case is the reference's sqrt(a*b)); oracle on a plane subset."""
+    case = Case("bar4", events_per_cam=300_000)
+    assert case.n_cams == 4 and case.method == 3
+    mappers = make_mappers(ctx, case)
+    planes = (0, 40, 128, 255)
+    per_cam = []
+    for i, m in enumerate(mappers):
+        m.build(case.events[i], case.packets[i])
+        counts = m.counts()
+        ref = _oracle_planes(O, case, i, planes)
+        per_cam.append(ref)
+        dsi = m.dsi_.download()
+        for k in planes:
+            assert counts[k] == ref[k][1]
+            np.testing.assert_allclose(dsi[k], ref[k][0], rtol=DSI_RTOL, atol=DSI_ATOL)
+        del dsi
+    fused = api.Grid3D(ctx, case.dimX, case.dimY, case.dimZ)
+    conf, idx, depth = api.fuse_collapse([m.dsi_ for m in mappers], 3, case.depths, fused_out=fused)
+    fz = fused.download()
+    for k in planes:
+        want = O.fuse_nary(3, [per_cam[i][k][0][None] for i in range(4)])[0]
+        np.testing.assert_allclose(fz[k], want, rtol=MAP_RTOL, atol=1e-5)
+    # the maps are consistent with the fused volume the GPU produced
+    assert np.array_equal(conf, fz.max(axis=0)) and np.array_equal(idx, fz.argmax(axis=0).astype(np.uint8))
+    assert np.array_equal(depth, case.depths[idx])
+    # n = 2 of the extension is the reference op
+    two = api.fuse_collapse([mappers[0].dsi_, mappers[1].dsi_], 3, fused_out=fused)
+    a, b = mappers[0].dsi_.download(), mappers[1].dsi_.download()
+    assert fused.download().tobytes() == O.fuse_reference(3, [a, b]).tobytes()
+    for m in mappers:
+        m.close()
+    fused.close()
+
+
+@pytest.mark.parametrize("dims,n_ev", [((256, 256, 128), 200_000), ((1024, 1024, 512), 150_000)])
+def test_config5_sweep_corners(ctx, O, dims, n_ev):
+    """Smallest and largest DSI of BASELINE.json configs[4] (1024^2 x 512 needs uint16 indices: extension)."""
+    from dvs_mcemvs_b200 import synth
+    W, H, Nz = dims
+    cam = api.CameraModel(W, H, 0.8 * W, 0.8 * W, W / 2.0, H / 2.0)
+    shape = api.ShapeDSI(0, 0, Nz, 1.0, 10.0, 0.0)
+    sc = synth.Scene(synth.Rig([cam], [0.0]), shape, duration=0.2, translation=(0.2, 0.0, 0.0), rot_deg=1.0, seed=5)
+    ev, traj = sc.events(0, n_ev), sc.trajectory(0)
+    m = api.MapperEMVS(ctx, cam, shape)
+    assert m.evaluateDSI(ev, api.LinearTrajectory(traj), sc.T_rv_w())
+    depths, virt = m.raw_depths_vec_, m.virtual_cam_
+    assert depths.tobytes() == O.depth_vector(1.0, 10.0, Nz).tobytes()
+    pk = O.packetize(ev, traj, sc.T_rv_w(), np.array([cam.fx, cam.fy, cam.cx, cam.cy], np.float32), virt, depths[0])
+    counts = m.counts()
+    dsi = m.dsi_.download()
+    np.testing.assert_allclose(dsi.reshape(Nz, -1).sum(1, dtype=np.float64), counts.astype(np.float64), rtol=2e-5)
+    for k in (0, Nz // 3, Nz - 1):
+        sel = np.array([depths[0], depths[k]], np.float32)
+        dsi_o, inb_o = O.build_dsi(ev, pk, cam.lut, W, sel, virt, W, H)
+        assert inb_o[1] == counts[k]
+        np.testing.assert_allclose(dsi[k], dsi_o[1], rtol=DSI_RTOL, atol=DSI_ATOL)
+    conf, idx, depth = m.dsi_.collapseMaxZSlice(depths)
+    assert idx.dtype == (np.uint8 if Nz <= 256 else np.uint16)
+    assert np.array_equal(conf, dsi.max(axis=0)) and np.array_equal(idx, dsi.argmax(axis=0).astype(idx.dtype))
+    assert np.array_equal(depth, depths[idx])
+    m.close()
