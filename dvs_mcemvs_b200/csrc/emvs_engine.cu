@@ -303,24 +303,12 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
 {
   const unsigned blocks = (n_pix + 127) / 128;
   cudaStream_t st = ctx->stream;
-  // 16-byte path: plane size a multiple of 4 voxels and every pointer 16-byte aligned.
-  // EMVS_FC_ZGROUPS (tuning): 0 = scalar kernel, 1/2/4 = Z-groups of the vectorised kernel.
-  static const int zg_env = [] { const char* e = getenv("EMVS_FC_ZGROUPS"); return e ? atoi(e) : 4; }();
-  bool vec = zg_env > 0 && (n_pix % 4u) == 0 && dimZ >= 4u;
-  auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  for (int i = 0; i < A.n; ++i) vec = vec && aligned16(A.g[i]);
-  vec = vec && aligned16(fused) && aligned16(conf) && aligned16(depth) && (reinterpret_cast<uintptr_t>(idx) & 7u) == 0;
-  const unsigned vblocks = (n_pix / 4 + 31) / 32;
-#define LAUNCH_V(M, N)                                                                                                  \
-  do {                                                                                                                 \
-    if (!vec) k_fuse_collapse<M, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
-    else if (zg_env == 1) k_fuse_collapse_v4<M, N, 1><<<vblocks, 32, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
-    else if (zg_env == 2) k_fuse_collapse_v4<M, N, 2><<<vblocks, 64, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
-    else k_fuse_collapse_v4<M, N, 4><<<vblocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); \
-  } while (0)
-#define LAUNCH(N) LAUNCH_V(METHOD, N)
+  // (A float4-per-thread variant with the Z range split over warps was measured slower than this
+  // one-pixel-per-thread sweep — 0.234 vs 0.209 ms for two 640x480x256 volumes, profiles/r1_fuse_collapse.md.)
+#define LAUNCH(N) \
+  k_fuse_collapse<METHOD, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth)
   switch (A.n) {
-    case 1: LAUNCH_V(EMVS_FUSE_MAX, 1); break;
+    case 1: k_fuse_collapse<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); break;
     case 2: LAUNCH(2); break;
     case 3: LAUNCH(3); break;
     case 4: LAUNCH(4); break;
@@ -331,7 +319,6 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
     default: set_error("fuse_collapse: need 1..8 grids"); return EMVS_ERR_INVALID;
   }
 #undef LAUNCH
-#undef LAUNCH_V
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return EMVS_OK;
@@ -942,24 +929,33 @@ static int check_packets(const emvs_packet* pk, size_t n_packets, size_t n_event
 // d_events is read by k_warp_events only; d_packets is read by every vote launch, hence two
 // alternating packet buffers: build N+2 can only upload after k_warp_events of build N+1 ran,
 // which is stream-ordered behind the last vote of build N.
+static int upload_events(emvs_context* ctx, const emvs_event* events, size_t n_events, size_t lo, size_t hi)
+{
+  int rc = grow(&ctx->d_events, &ctx->events_cap, n_events * sizeof(emvs_event));
+  if (rc) return rc;
+  if (ctx->consumed_recorded) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed, 0));
+  CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + lo, events + lo, (hi - lo) * sizeof(emvs_event),
+                           cudaMemcpyHostToDevice, ctx->copy_stream));
+  return EMVS_OK;
+}
+
 static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
-                           size_t n_packets, int flags)
+                           size_t n_packets, int flags, bool events_uploaded)
 {
   emvs_context* ctx = m->ctx;
   const unsigned par = ctx->build_parity++ & 1u;
   if (n_packets) {
-    size_t lo = n_events, last = 0;   // only the span of events that packets reference has to travel
-    for (size_t j = 0; j < n_packets; ++j) {
-      lo = std::min<size_t>(lo, packets[j].first_event);
-      last = std::max<size_t>(last, packets[j].first_event + EMVS_PACKET_SIZE);
+    if (!events_uploaded) {
+      size_t lo = n_events, last = 0;   // only the span of events that packets reference has to travel
+      for (size_t j = 0; j < n_packets; ++j) {
+        lo = std::min<size_t>(lo, packets[j].first_event);
+        last = std::max<size_t>(last, packets[j].first_event + EMVS_PACKET_SIZE);
+      }
+      const int rc = upload_events(ctx, events, n_events, lo, last);
+      if (rc) return rc;
     }
-    int rc = grow(&ctx->d_events, &ctx->events_cap, n_events * sizeof(emvs_event));
+    const int rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par], n_packets * sizeof(emvs_packet));
     if (rc) return rc;
-    rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par], n_packets * sizeof(emvs_packet));
-    if (rc) return rc;
-    if (ctx->consumed_recorded) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed, 0));
-    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + lo, events + lo, (last - lo) * sizeof(emvs_event),
-                             cudaMemcpyHostToDevice, ctx->copy_stream));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], packets, n_packets * sizeof(emvs_packet), cudaMemcpyHostToDevice,
                              ctx->copy_stream));
     CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
@@ -983,7 +979,7 @@ int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events,
   int rc = check_packets(packets, n_packets, n_events);
   if (rc) return rc;
   DeviceGuard guard(m->ctx->device);
-  return build_from_host(m, events, n_events, packets, n_packets, flags);
+  return build_from_host(m, events, n_events, packets, n_packets, flags, false);
 }
 
 int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_events, const void* d_packets,
@@ -1015,9 +1011,17 @@ int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_
     CUDA_TRY(cudaHostAlloc((void**)&ctx->h_packets, max_pk * sizeof(emvs_packet), cudaHostAllocDefault));
     ctx->h_packets_cap = max_pk;
   }
+  REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi: rectification LUT not set (emvs_mapper_set_lut)");
+  // start the event upload first: the host packet stage (one pose + one 3x3 inverse per 1024
+  // events) then runs while the copy engine is busy
+  int rc = upload_events(ctx, events, n_events, 0, n_events);
+  if (rc) return rc;
   const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
                                      ctx->h_packets, max_pk);
-  return emvs_mapper_build(m, events, n_events, ctx->h_packets, n_pk, EMVS_BUILD_RESET);
+  rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, EMVS_BUILD_RESET, true);
+  if (rc) return rc;
+  if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // nothing waited for the event upload
+  return EMVS_OK;
 }
 
 int emvs_mapper_counts(const emvs_mapper* m, uint64_t* per_plane)

@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--cpu-events", type=int, default=200_000)
+    ap.add_argument("--cpu-events", type=int, default=1_000_000)
     a = ap.parse_args()
     import torch
     from dvs_mcemvs_b200 import api, synth
