@@ -60,9 +60,16 @@ struct emvs_context {
   int sm_count = 148;
   uint64_t launches = 0;
   uint32_t slab_override = 0;
-  // quad scratch for one slab of planes; invariant: all zero between builds
-  float4* quad = nullptr;
-  size_t quad_bytes = 0;
+  // Quad scratch: two buffers of one slab of planes each (invariant: all zero between builds).
+  // Slab s is voted into buffer s&1 on `stream` while buffer (s-1)&1 is merged into the DSI and
+  // re-zeroed on `aux_stream` (EMVS_OVERLAP=0 serialises everything on `stream` with one buffer).
+  float4* quad[2] = {nullptr, nullptr};
+  size_t quad_bytes[2] = {0, 0};
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_vote[2] = {nullptr, nullptr};    // slab voted into buffer b
+  cudaEvent_t ev_merge[2] = {nullptr, nullptr};   // buffer b merged + zeroed again
+  bool merge_pending[2] = {false, false};
+  bool overlap = true;
   // grow-only device staging
   void* d_events = nullptr;  size_t events_cap = 0;
   void* d_packets[2] = {nullptr, nullptr}; size_t packets_cap[2] = {0, 0};  // alternate per build (see build_from_host)
@@ -152,7 +159,7 @@ uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint
   }
   if (!s) {
     const size_t plane_bytes = (size_t)ceil_div(dimX, 2) * ceil_div(dimY, 2) * 64;
-    const size_t budget = (size_t)80 << 20;
+    const size_t budget = ((size_t)80 << 20) / (ctx->overlap ? 2 : 1);   // both buffers share the L2 budget
     s = (uint32_t)std::max<size_t>(1, budget / std::max<size_t>(plane_bytes, 1));
   }
   s = std::min(s, dimZ);
@@ -160,15 +167,15 @@ uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint
   return std::max<uint32_t>(s, 1);
 }
 
-int ensure_quad(emvs_context* ctx, size_t bytes)
+int ensure_quad(emvs_context* ctx, int b, size_t bytes)
 {
-  if (bytes <= ctx->quad_bytes) return EMVS_OK;
-  if (ctx->quad) CUDA_TRY(cudaFree(ctx->quad));
-  ctx->quad = nullptr;
-  ctx->quad_bytes = 0;
-  CUDA_TRY(cudaMalloc((void**)&ctx->quad, bytes));
-  ctx->quad_bytes = bytes;
-  CUDA_TRY(cudaMemsetAsync(ctx->quad, 0, bytes, ctx->stream));
+  if (bytes <= ctx->quad_bytes[b]) return EMVS_OK;
+  if (ctx->quad[b]) CUDA_TRY(cudaFree(ctx->quad[b]));   // cudaFree waits for the device: no kernel still uses it
+  ctx->quad[b] = nullptr;
+  ctx->quad_bytes[b] = 0;
+  CUDA_TRY(cudaMalloc((void**)&ctx->quad[b], bytes));
+  ctx->quad_bytes[b] = bytes;
+  CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, bytes, ctx->stream));
   return EMVS_OK;
 }
 
@@ -223,8 +230,9 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   const uint32_t QW = ceil_div(dimX, 2), QH = ceil_div(dimY, 2);
   const uint32_t slab = choose_slab(ctx, dimX, dimY, dimZ);
   const size_t slab_bytes = (size_t)slab * QW * QH * 4 * sizeof(float4);
-  {
-    const int rc = ensure_quad(ctx, slab_bytes);
+  const bool overlap = ctx->overlap;
+  for (int b = 0; b < (overlap ? 2 : 1); ++b) {
+    const int rc = ensure_quad(ctx, b, slab_bytes);
     if (rc) return rc;
   }
 
@@ -249,6 +257,12 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   for (uint32_t k0 = 0; k0 < dimZ; k0 += slab) {
     const uint32_t nk = std::min(slab, dimZ - k0);
     const size_t smem = nk * (sizeof(float4) + sizeof(unsigned int));
+    const int b = overlap ? (int)((k0 / slab) & 1u) : 0;
+    cudaStream_t ms = overlap ? ctx->aux_stream : st;   // merge + re-zero stream
+    if (overlap && ctx->merge_pending[b]) {             // buffer b must be merged and zero again (slab s-2)
+      CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_merge[b], 0));
+      ctx->merge_pending[b] = false;
+    }
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) {
       if (ctx->prof_used + 2 > ctx->prof_events.size()) {
@@ -263,15 +277,23 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       ctx->prof_used += 2;
       CUDA_TRY(cudaEventRecord(pe0, st));
     }
-    k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad,
+    k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
                                                             m->d_counts);
     ctx->launches++;
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
+    if (overlap) {
+      CUDA_TRY(cudaEventRecord(ctx->ev_vote[b], st));
+      CUDA_TRY(cudaStreamWaitEvent(ms, ctx->ev_vote[b], 0));
+    }
     dim3 mb(32, 8, 1), mg(ceil_div(QW, 32), ceil_div(QH, 8), nk);
-    k_merge_quads<<<mg, mb, 0, st>>>(ctx->quad, g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
+    k_merge_quads<<<mg, mb, 0, ms>>>(ctx->quad[b], g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
                                      accumulate ? 1 : 0);
     ctx->launches++;
-    CUDA_TRY(cudaMemsetAsync(ctx->quad, 0, (size_t)nk * QW * QH * 4 * sizeof(float4), st));
+    CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, (size_t)nk * QW * QH * 4 * sizeof(float4), ms));
+    if (overlap) {
+      CUDA_TRY(cudaEventRecord(ctx->ev_merge[b], ms));
+      ctx->merge_pending[b] = true;
+    }
     if (reduce) {
       // planes [k0, k0+nk) are final on this rank: sum them over the ranks on the communication
       // stream while the next slab is being voted
@@ -281,12 +303,18 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->slab_events.push_back(e);
       }
-      CUDA_TRY(cudaEventRecord(ctx->slab_events[si], st));
+      CUDA_TRY(cudaEventRecord(ctx->slab_events[si], ms));
       CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->slab_events[si], 0));
       if (ncclAllReduce_checked(nccl, ctx, g->d + (size_t)k0 * dimX * dimY, (size_t)nk * dimX * dimY, ctx->comm_stream))
         return EMVS_ERR_NCCL;
     }
   }
+  // everything later on `stream` (fusion, download, the next build) sees the finished DSI
+  for (int b = 0; b < 2; ++b)
+    if (ctx->merge_pending[b]) {
+      CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_merge[b], 0));
+      ctx->merge_pending[b] = false;
+    }
   if (reduce) {
     // the vote counters are final once the last vote kernel ran (recorded by the last slab event)
     if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, dimZ, ctx->comm_stream)) return EMVS_ERR_NCCL;
@@ -404,6 +432,12 @@ int emvs_context_create(int device, emvs_context** out)
   ctx->sm_count = prop.multiProcessorCount;
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    e = cudaEventCreateWithFlags(&ctx->ev_vote[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_merge[b], cudaEventDisableTiming);
+  }
+  if (const char* env = getenv("EMVS_OVERLAP")) ctx->overlap = atoi(env) != 0;
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_partial, sizeof(double) * 1025);
@@ -433,7 +467,14 @@ static void context_release(emvs_context* ctx)
   DeviceGuard guard(ctx->device);
   if (ctx->comm) emvs_comm_destroy(ctx);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->quad);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+  cudaFree(ctx->quad[0]);
+  cudaFree(ctx->quad[1]);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->ev_vote[b]) cudaEventDestroy(ctx->ev_vote[b]);
+    if (ctx->ev_merge[b]) cudaEventDestroy(ctx->ev_merge[b]);
+  }
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   cudaFree(ctx->d_events);
   cudaFree(ctx->d_packets[0]);
