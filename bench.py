@@ -59,6 +59,9 @@ def parse_args():
                     help="events per camera of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU DSI exchange: fused reduce+fuse+argmax over NVLink peer memory, or "
+                         "slab-wise ncclAllReduce overlapped with voting followed by a local sweep")
     return ap.parse_args()
 
 
@@ -260,10 +263,21 @@ def run_b200(args):
     def collapse_device():
         api.fuse_collapse_device(grids, method, d_tab, d_conf.data_ptr(), d_idx.data_ptr(), d_depth.data_ptr())
 
+    peer = None
+    if world > 1 and args.exchange == "peer":
+        def allgather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        peer = api.PeerExchange(ctx, grids, world, rank, allgather)
+
     def step_device():
         for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
-            m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1)
-        collapse_device()
+            m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None)
+        if peer is not None:
+            peer.fuse_collapse(method, d_tab)
+        else:
+            collapse_device()
 
     t_all, t_build, t_depth = ctx.timer(), ctx.timer(), ctx.timer()
 
@@ -318,10 +332,13 @@ def run_b200(args):
 
         def step_host():
             for m, ev, tr in zip(mappers, h_events, ltrajs):
-                if world > 1:   # sharded: host packet stage, then this rank's build with slab-wise allreduce
+                if world > 1 and peer is None:   # sharded: host packet stage, then this rank's build with slab-wise allreduce
                     m.build(ev, m.packetize(ev, tr, T_rv_w), allreduce=True)
                 else:
                     assert m.evaluateDSI(ev, tr, T_rv_w)
+            if peer is not None:
+                peer.fuse_collapse(method, d_tab)
+                return peer.download()
             return api.fuse_collapse([m.dsi_ for m in mappers], method, depths)
 
         for _ in range(max(1, min(args.warmup, 2))):
@@ -384,7 +401,10 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "description": desc, "events_per_camera_per_gpu": n_ev, "cameras": n_cams,
                        "dsi": [dimX, dimY, dimZ], "fusion": "harmonic", "event_distribution": args.kind,
-                       "sharding": "event sub-interval per GPU; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting" if world > 1 else "none",
+                       "sharding": ("none" if world == 1 else
+                                    "event sub-interval per GPU; fused reduce+fuse+argmax sweep over NVLink peer memory (row band per GPU)"
+                                    if peer is not None else
+                                    "event sub-interval per GPU; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting"),
                        "l2": "inputs+DSIs (>700 MB/step) exceed the 126 MB L2; no explicit flush"},
             "build_mevents_per_s": n_cams * n_ev / (build_ms * 1e-3) / 1e6, "build_ms": build_ms,
             "depth_map_ms": depth_ms, "accepted_votes_per_step": votes,
@@ -394,6 +414,10 @@ def run_b200(args):
             out["cpu_baseline"], _ = cpu_reference(args, n_ev)
         _emit(json.dumps(out))
     if world > 1:
+        if peer is not None:
+            ctx.sync()
+            dist.barrier()
+            peer.close()
         ctx.comm_destroy()
         dist.destroy_process_group()
 

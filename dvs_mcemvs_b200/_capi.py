@@ -105,6 +105,14 @@ _PROTOTYPES = {
     "emvs_grid_allreduce": (C.c_int, [_vp]),
     "emvs_grid_allreduce_async": (C.c_int, [_vp]),
     "emvs_mapper_counts_allreduce": (C.c_int, [_vp]),
+    "emvs_exchange_create": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "emvs_exchange_destroy": (C.c_int, [_vp]),
+    "emvs_exchange_blob_bytes": (C.c_int, [_vp, C.POINTER(_sz)]),
+    "emvs_exchange_export": (C.c_int, [_vp, _vp]),
+    "emvs_exchange_import": (C.c_int, [_vp, _vp]),
+    "emvs_exchange_fuse_collapse": (C.c_int, [_vp, C.c_int, _vp]),
+    "emvs_exchange_maps": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "emvs_exchange_download": (C.c_int, [_vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -308,6 +308,49 @@ def fuse_collapse_device(grids, method, d_depths, d_conf, d_idx, d_depth, fused_
                                            C.c_void_p(d_idx), C.c_void_p(d_depth) if d_depth else None))
 
 
+class PeerExchange:
+    """Fused multi-GPU reduce + fuse + argmax over NVLink peer memory (emvs_exchange_*).
+
+    grids: this rank's partial DSIs, one per camera (same order on every rank).
+    allgather: callable(bytes) -> list of every rank's bytes in rank order (e.g. built on
+    torch.distributed.all_gather_object); used once to exchange the CUDA IPC handles."""
+
+    def __init__(self, ctx, grids, n_ranks, rank, allgather):
+        self.ctx, self.grids = ctx, list(grids)
+        arr = (C.c_void_p * len(grids))(*[g._h for g in grids])
+        h = C.c_void_p()
+        check(_lib().emvs_exchange_create(ctx._h, arr, len(grids), int(n_ranks), int(rank), C.byref(h)))
+        self._h = h
+        self.size_ = grids[0].size_
+        n = C.c_size_t(0)
+        check(_lib().emvs_exchange_blob_bytes(self._h, C.byref(n)))
+        blob = np.zeros(n.value, np.uint8)
+        check(_lib().emvs_exchange_export(self._h, ptr(blob)))
+        blobs = allgather(blob.tobytes())
+        assert len(blobs) == n_ranks and all(len(b) == n.value for b in blobs)
+        cat = np.frombuffer(b"".join(blobs), np.uint8).copy()
+        check(_lib().emvs_exchange_import(self._h, ptr(cat)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().emvs_exchange_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def fuse_collapse(self, method, d_depths=None):
+        """Collective and asynchronous: call on every rank after its builds were issued."""
+        check(_lib().emvs_exchange_fuse_collapse(self._h, int(method), C.c_void_p(d_depths) if d_depths else None))
+
+    def download(self, with_depth=True):
+        dimX, dimY, dimZ = self.size_
+        conf = np.empty((dimY, dimX), np.float32)
+        idx = np.empty((dimY, dimX), np.uint8 if dimZ <= 256 else np.uint16)
+        depth = np.empty((dimY, dimX), np.float32) if with_depth else None
+        check(_lib().emvs_exchange_download(self._h, ptr(conf), ptr(idx), ptr(depth)))
+        return (conf, idx, depth) if with_depth else (conf, idx)
+
+
 class MapperEMVS:
     """EMVS::MapperEMVS(cam, dsi_shape) — mapper_emvs_stereo.hpp:94-155."""
 

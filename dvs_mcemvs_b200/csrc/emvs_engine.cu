@@ -1174,4 +1174,232 @@ int emvs_mapper_counts_allreduce(emvs_mapper* m)
   return EMVS_OK;
 }
 
+// ---- fused multi-GPU sweep over peer memory ------------------------------------------------------
+struct emvs_exchange {
+  emvs_context* ctx = nullptr;
+  int n_cams = 0, n_ranks = 1, rank = 0;
+  uint32_t dimX = 0, dimY = 0, dimZ = 0;
+  const float* local_dsi[kMaxPeerCams] = {};
+  char* maps = nullptr;            // conf | depth | idx of this rank (one allocation, IPC-exported)
+  size_t off_depth = 0, off_idx = 0, maps_bytes = 0;
+  unsigned int* flags = nullptr;   // [2][kMaxPeerRanks] epochs + 1 error word (IPC-exported)
+  PeerArgs args{};
+  FlagPtrs flag_ptrs{};
+  std::vector<void*> opened;       // cudaIpcOpenMemHandle mappings to close
+  unsigned int epoch = 0;
+  bool imported = false;
+};
+
+static const size_t kIpcBytes = sizeof(cudaIpcMemHandle_t);
+
+int emvs_exchange_create(emvs_context* ctx, emvs_grid* const* grids, int n_cams, int n_ranks, int rank, emvs_exchange** out)
+{
+  REQUIRE(ctx && grids && out, EMVS_ERR_INVALID, "exchange_create: NULL argument");
+  *out = nullptr;
+  REQUIRE(n_cams >= 1 && n_cams <= kMaxPeerCams, EMVS_ERR_INVALID, "exchange_create: need 1..4 cameras");
+  REQUIRE(n_ranks >= 1 && n_ranks <= kMaxPeerRanks && rank >= 0 && rank < n_ranks, EMVS_ERR_INVALID,
+          "exchange_create: need 1..8 ranks and 0 <= rank < n_ranks");
+  for (int c = 0; c < n_cams; ++c) {
+    REQUIRE(grids[c] && grids[c]->ctx == ctx, EMVS_ERR_INVALID, "exchange_create: grid of another context");
+    REQUIRE(same_dims(grids[0], grids[c]), EMVS_ERR_INVALID, "exchange_create: grids differ in shape");
+  }
+  DeviceGuard guard(ctx->device);
+  emvs_exchange* ex = new (std::nothrow) emvs_exchange;
+  REQUIRE(ex, EMVS_ERR_INVALID, "out of host memory");
+  ex->ctx = ctx;
+  ex->n_cams = n_cams; ex->n_ranks = n_ranks; ex->rank = rank;
+  ex->dimX = grids[0]->dimX; ex->dimY = grids[0]->dimY; ex->dimZ = grids[0]->dimZ;
+  for (int c = 0; c < n_cams; ++c) ex->local_dsi[c] = grids[c]->d;
+  const size_t n_pix = (size_t)ex->dimX * ex->dimY;
+  ex->off_depth = n_pix * 4;
+  ex->off_idx = n_pix * 8;
+  ex->maps_bytes = n_pix * 10;
+  cudaError_t e = cudaMalloc((void**)&ex->maps, ex->maps_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ex->flags, sizeof(unsigned int) * (2 * kMaxPeerRanks + 1));
+  if (e == cudaSuccess) e = cudaMemset(ex->flags, 0, sizeof(unsigned int) * (2 * kMaxPeerRanks + 1));
+  if (e == cudaSuccess) e = cudaMemset(ex->maps, 0, ex->maps_bytes);
+  if (e != cudaSuccess) {
+    set_error("exchange_create: %s", cudaGetErrorString(e));
+    cudaFree(ex->maps);
+    cudaFree(ex->flags);
+    delete ex;
+    return EMVS_ERR_CUDA;
+  }
+  context_retain(ctx);
+  *out = ex;
+  return EMVS_OK;
+}
+
+int emvs_exchange_destroy(emvs_exchange* ex)
+{
+  if (!ex) return EMVS_OK;
+  DeviceGuard guard(ex->ctx->device);
+  cudaStreamSynchronize(ex->ctx->stream);
+  for (void* p : ex->opened) cudaIpcCloseMemHandle(p);
+  cudaFree(ex->maps);
+  cudaFree(ex->flags);
+  context_release(ex->ctx);
+  delete ex;
+  return EMVS_OK;
+}
+
+int emvs_exchange_blob_bytes(const emvs_exchange* ex, size_t* out)
+{
+  REQUIRE(ex && out, EMVS_ERR_INVALID, "exchange_blob_bytes: NULL argument");
+  *out = kIpcBytes * (size_t)(ex->n_cams + 2);
+  return EMVS_OK;
+}
+
+int emvs_exchange_export(emvs_exchange* ex, uint8_t* blob)
+{
+  REQUIRE(ex && blob, EMVS_ERR_INVALID, "exchange_export: NULL argument");
+  DeviceGuard guard(ex->ctx->device);
+  cudaIpcMemHandle_t h;
+  for (int c = 0; c < ex->n_cams; ++c) {
+    CUDA_TRY(cudaIpcGetMemHandle(&h, (void*)ex->local_dsi[c]));
+    memcpy(blob + kIpcBytes * c, &h, kIpcBytes);
+  }
+  CUDA_TRY(cudaIpcGetMemHandle(&h, ex->maps));
+  memcpy(blob + kIpcBytes * ex->n_cams, &h, kIpcBytes);
+  CUDA_TRY(cudaIpcGetMemHandle(&h, ex->flags));
+  memcpy(blob + kIpcBytes * (ex->n_cams + 1), &h, kIpcBytes);
+  return EMVS_OK;
+}
+
+int emvs_exchange_import(emvs_exchange* ex, const uint8_t* all)
+{
+  REQUIRE(ex && all, EMVS_ERR_INVALID, "exchange_import: NULL argument");
+  REQUIRE(!ex->imported, EMVS_ERR_STATE, "exchange_import: already imported");
+  DeviceGuard guard(ex->ctx->device);
+  const size_t per_rank = kIpcBytes * (size_t)(ex->n_cams + 2);
+  const size_t n_pix = (size_t)ex->dimX * ex->dimY;
+  (void)n_pix;
+  PeerArgs& A = ex->args;
+  A.n_cams = ex->n_cams;
+  A.n_ranks = ex->n_ranks;
+  for (int r = 0; r < ex->n_ranks; ++r) {
+    char* maps = nullptr;
+    unsigned int* flags = nullptr;
+    if (r == ex->rank) {
+      for (int c = 0; c < ex->n_cams; ++c) A.dsi[c][r] = ex->local_dsi[c];
+      maps = ex->maps;
+      flags = ex->flags;
+    } else {
+      const uint8_t* b = all + per_rank * r;
+      cudaIpcMemHandle_t h;
+      void* p = nullptr;
+      for (int c = 0; c < ex->n_cams; ++c) {
+        memcpy(&h, b + kIpcBytes * c, kIpcBytes);
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ex->opened.push_back(p);
+        A.dsi[c][r] = (const float*)p;
+      }
+      memcpy(&h, b + kIpcBytes * ex->n_cams, kIpcBytes);
+      CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      ex->opened.push_back(p);
+      maps = (char*)p;
+      memcpy(&h, b + kIpcBytes * (ex->n_cams + 1), kIpcBytes);
+      CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      ex->opened.push_back(p);
+      flags = (unsigned int*)p;
+    }
+    A.conf[r] = (float*)maps;
+    A.depth[r] = (float*)(maps + ex->off_depth);
+    A.idx[r] = maps + ex->off_idx;
+    ex->flag_ptrs.p[r] = flags;
+  }
+  ex->imported = true;
+  return EMVS_OK;
+}
+
+}  // extern "C" (templates cannot have C linkage)
+
+template <int METHOD>
+static int launch_peer(emvs_exchange* ex, const float* d_depths, uint32_t p_lo, uint32_t p_hi, long long timeout)
+{
+  emvs_context* ctx = ex->ctx;
+  const uint32_t n_pix = ex->dimX * ex->dimY;
+  const unsigned blocks = (p_hi - p_lo + 127) / 128;
+  const int idx_bytes = ex->dimZ <= 256 ? 1 : 2;
+  unsigned int* err = ex->flags + 2 * kMaxPeerRanks;
+#define LAUNCH(N)                                                                                                       \
+  k_fuse_collapse_peer<METHOD, N><<<blocks, 128, 0, ctx->stream>>>(ex->args, ex->flags, ex->epoch, timeout, err, p_lo, p_hi, \
+                                                                   n_pix, ex->dimZ, d_depths, idx_bytes)
+  switch (ex->n_cams) {
+    case 1: k_fuse_collapse_peer<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, ctx->stream>>>(ex->args, ex->flags, ex->epoch, timeout, err,
+                                                                                  p_lo, p_hi, n_pix, ex->dimZ, d_depths, idx_bytes); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    default: break;
+  }
+#undef LAUNCH
+  ctx->launches++;
+  return EMVS_OK;
+}
+
+extern "C" {
+
+int emvs_exchange_fuse_collapse(emvs_exchange* ex, int method, const float* d_depths)
+{
+  REQUIRE(ex, EMVS_ERR_INVALID, "exchange is NULL");
+  REQUIRE(ex->imported, EMVS_ERR_STATE, "exchange_fuse_collapse: peers not imported (emvs_exchange_import)");
+  REQUIRE(method >= EMVS_FUSE_MIN && method <= EMVS_FUSE_MAX, EMVS_ERR_INVALID, "Improper fusion method selected");
+  emvs_context* ctx = ex->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  ex->epoch++;
+  ex->args.method = method;
+  // ~20 s at 2 GHz: a peer that never arrives raises the error word instead of hanging the GPU
+  const long long timeout = 40000000000LL;
+  // rows owned by this rank (balanced to within one row)
+  const uint32_t base = ex->dimY / ex->n_ranks, extra = ex->dimY % ex->n_ranks;
+  const uint32_t row_lo = ex->rank * base + std::min<uint32_t>(ex->rank, extra);
+  const uint32_t row_hi = row_lo + base + ((uint32_t)ex->rank < extra ? 1u : 0u);
+  k_flag_signal<<<1, 32, 0, st>>>(ex->flag_ptrs, ex->n_ranks, ex->rank, 0, ex->epoch);   // "my partial DSIs are built"
+  ctx->launches++;
+  if (row_hi > row_lo) {
+    int rc = EMVS_OK;
+    switch (method) {
+      case EMVS_FUSE_MIN: rc = launch_peer<EMVS_FUSE_MIN>(ex, d_depths, row_lo * ex->dimX, row_hi * ex->dimX, timeout); break;
+      case EMVS_FUSE_HM: rc = launch_peer<EMVS_FUSE_HM>(ex, d_depths, row_lo * ex->dimX, row_hi * ex->dimX, timeout); break;
+      case EMVS_FUSE_GM: rc = launch_peer<EMVS_FUSE_GM>(ex, d_depths, row_lo * ex->dimX, row_hi * ex->dimX, timeout); break;
+      case EMVS_FUSE_AM: rc = launch_peer<EMVS_FUSE_AM>(ex, d_depths, row_lo * ex->dimX, row_hi * ex->dimX, timeout); break;
+      case EMVS_FUSE_RMS: rc = launch_peer<EMVS_FUSE_RMS>(ex, d_depths, row_lo * ex->dimX, row_hi * ex->dimX, timeout); break;
+      default: rc = launch_peer<EMVS_FUSE_MAX>(ex, d_depths, row_lo * ex->dimX, row_hi * ex->dimX, timeout); break;
+    }
+    if (rc) return rc;
+  }
+  k_flag_signal<<<1, 32, 0, st>>>(ex->flag_ptrs, ex->n_ranks, ex->rank, 1, ex->epoch);   // "my band is stored everywhere"
+  k_flag_wait<<<1, 32, 0, st>>>(ex->flags, ex->n_ranks, 1, ex->epoch, timeout, ex->flags + 2 * kMaxPeerRanks);
+  ctx->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return EMVS_OK;
+}
+
+int emvs_exchange_maps(const emvs_exchange* ex, float** d_conf, void** d_idx, float** d_depth)
+{
+  REQUIRE(ex, EMVS_ERR_INVALID, "exchange is NULL");
+  if (d_conf) *d_conf = (float*)ex->maps;
+  if (d_depth) *d_depth = (float*)(ex->maps + ex->off_depth);
+  if (d_idx) *d_idx = ex->maps + ex->off_idx;
+  return EMVS_OK;
+}
+
+int emvs_exchange_download(emvs_exchange* ex, float* conf, void* idx, float* depth)
+{
+  REQUIRE(ex, EMVS_ERR_INVALID, "exchange is NULL");
+  emvs_context* ctx = ex->ctx;
+  DeviceGuard guard(ctx->device);
+  const size_t n_pix = (size_t)ex->dimX * ex->dimY;
+  unsigned int err = 0;
+  if (conf) CUDA_TRY(cudaMemcpyAsync(conf, ex->maps, n_pix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (depth) CUDA_TRY(cudaMemcpyAsync(depth, ex->maps + ex->off_depth, n_pix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (idx) CUDA_TRY(cudaMemcpyAsync(idx, ex->maps + ex->off_idx, n_pix * (ex->dimZ <= 256 ? 1 : 2), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&err, ex->flags + 2 * kMaxPeerRanks, sizeof err, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  REQUIRE(err == 0, EMVS_ERR_STATE, "exchange: timed out waiting for a peer rank");
+  return EMVS_OK;
+}
+
 }  // extern "C"

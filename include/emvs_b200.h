@@ -267,6 +267,37 @@ EMVS_API int emvs_grid_allreduce_async(emvs_grid* g);
 /* Sum of the per-plane vote counts over all ranks. */
 EMVS_API int emvs_mapper_counts_allreduce(emvs_mapper* m);
 
+
+/* ---- multi-GPU, fused: reduce + fuse + argmax over NVLink peer memory ----------------------------
+ * Alternative to allreduce + emvs_fuse_collapse when only the depth / confidence maps are needed:
+ * rank r owns a band of image rows and reads the partial voxels of ALL ranks for that band
+ * directly from their HBM (CUDA IPC mappings, loads through NVSwitch), sums them in rank order,
+ * fuses the cameras, takes the Z-argmax and stores the result into the map buffers of every rank.
+ * The per-camera DSIs stay partial on every rank; no summed volume is written anywhere.
+ *
+ * Setup (collective, once): every rank creates an exchange over its n_cams partial grids (same
+ * shapes, same camera order), exports a blob of emvs_exchange_blob_bytes() bytes, the caller
+ * all-gathers the blobs (e.g. torch.distributed) and every rank imports the concatenation in rank
+ * order.  Per step (collective): after the local builds have been issued,
+ * emvs_exchange_fuse_collapse enqueues {signal "built", the fused sweep, signal "done", wait for
+ * all "done"} on the context's stream; when the stream reaches the end of that sequence the local
+ * map buffers hold the full maps and no peer reads this rank's DSIs any more (so they may be
+ * rebuilt).  A peer that never arrives is reported as EMVS_ERR_STATE by the next
+ * emvs_exchange_download after a timeout instead of hanging the GPU. */
+typedef struct emvs_exchange emvs_exchange;
+EMVS_API int emvs_exchange_create(emvs_context* ctx, emvs_grid* const* grids, int n_cams, int n_ranks, int rank,
+                         emvs_exchange** out);
+EMVS_API int emvs_exchange_destroy(emvs_exchange* ex);
+EMVS_API int emvs_exchange_blob_bytes(const emvs_exchange* ex, size_t* out);
+EMVS_API int emvs_exchange_export(emvs_exchange* ex, uint8_t* blob);
+EMVS_API int emvs_exchange_import(emvs_exchange* ex, const uint8_t* all_blobs /* n_ranks * blob_bytes */);
+/* method: EMVS_FUSE_*; d_depths: DEVICE depth table (emvs_mapper_depths_device) or NULL. */
+EMVS_API int emvs_exchange_fuse_collapse(emvs_exchange* ex, int method, const float* d_depths);
+/* Device pointers of this rank's map buffers (conf f32, idx u8|u16, depth f32; dimY*dimX each). */
+EMVS_API int emvs_exchange_maps(const emvs_exchange* ex, float** d_conf, void** d_idx, float** d_depth);
+/* Waits for the pipeline and copies the maps to the host (any pointer may be NULL). */
+EMVS_API int emvs_exchange_download(emvs_exchange* ex, float* conf, void* idx, float* depth);
+
 #ifdef __cplusplus
 }
 #endif

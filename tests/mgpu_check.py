@@ -33,6 +33,11 @@ def main():
     dist.broadcast(idt, 0)
     ctx.comm_init(idt.cpu().numpy().tobytes(), world, rank)
 
+    def allgather(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
     for name, n_ev, overlapped in (("esim_small", 50_000, False), ("esim_small", 50_000, True),
                                    ("dsec_stereo", 400_000, True)):
         sc, _, method, _ = synth.config(name, events_per_cam=n_ev)
@@ -42,6 +47,15 @@ def main():
         T = sc.T_rv_w()
         mappers = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
         packets = [m.packetize(ev, tr, T) for m, ev, tr in zip(mappers, events, trajs)]
+        # (a) fused path: partial DSIs stay partial, one sweep over peer memory produces the maps
+        ex = api.PeerExchange(ctx, [m.dsi_ for m in mappers], world, rank, allgather)
+        for rep in range(2):   # twice: the epoch flags must work repeatedly
+            for cam, lo, hi in shard.plan([len(p) for p in packets], world, rank):
+                mappers[cam].build(events[cam], packets[cam][lo:hi])
+            ex.fuse_collapse(method, mappers[0].depths_device_ptr())
+            conf_p, idx_p, depth_p = ex.download()
+        ex.close()
+        # (b) allreduce paths
         for cam, lo, hi in shard.plan([len(p) for p in packets], world, rank):
             if overlapped:   # EMVS_BUILD_ALLREDUCE: every Z-slab is summed while the next one is voted
                 mappers[cam].build(events[cam], packets[cam][lo:hi], allreduce=True)
@@ -61,12 +75,18 @@ def main():
             np.testing.assert_allclose(conf, conf_f, rtol=1e-4, atol=1e-6)
             agree = float((idx == idx_f).mean())
             assert agree > 0.999, agree
+            np.testing.assert_allclose(conf_p, conf_f, rtol=1e-4, atol=1e-6)   # fused peer sweep
+            agree_p = float((idx_p == idx_f).mean())
+            assert agree_p > 0.999, agree_p
+            same = idx_p == idx_f
+            assert np.array_equal(depth_p[same], depth_f[same])
             print(f"mgpu_check {name} overlapped={overlapped}: world={world} counts exact, conf within 1e-4, index agreement {agree:.5f}")
         # all ranks hold identical maps after the allreduce (same summands, same NCCL reduction order)
-        t = torch.from_numpy(conf.copy()).cuda()
-        ref = t.clone()
-        dist.broadcast(ref, 0)
-        assert torch.equal(t, ref), "ranks disagree on the confidence map"
+        for arr, what in ((conf, "allreduce"), (conf_p, "peer sweep")):
+            t = torch.from_numpy(arr.copy()).cuda()
+            ref = t.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(t, ref), f"ranks disagree on the confidence map ({what})"
         for m in mappers:
             m.close()
     ctx.comm_destroy()
