@@ -150,7 +150,8 @@ inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 // Planes voted per pass over the event list.  The quad scratch of a slab (4 copies) must stay
 // L2-resident together with the streaming event reads.  Measured on B200 (126 MB L2) at
 // 640x480: 16 planes (79 MB) is the fastest, 32 planes (157 MB) falls off the L2 cliff
-// (profiles/r1_slab_sweep.md); 80 MiB is the budget.
+// (profiles/r1_slab_sweep.md).  With the double-buffered scratch (merge of slab s overlapped with
+// the votes of slab s+1) 2 x 12 planes (118 MB) measured fastest: 59 MiB per buffer.
 uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ)
 {
   uint32_t s = ctx->slab_override;
@@ -159,7 +160,7 @@ uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint
   }
   if (!s) {
     const size_t plane_bytes = (size_t)ceil_div(dimX, 2) * ceil_div(dimY, 2) * 64;
-    const size_t budget = ((size_t)80 << 20) / (ctx->overlap ? 2 : 1);   // both buffers share the L2 budget
+    const size_t budget = ctx->overlap ? ((size_t)59 << 20) : ((size_t)80 << 20);   // per buffer; two buffers when overlapped
     s = (uint32_t)std::max<size_t>(1, budget / std::max<size_t>(plane_bytes, 1));
   }
   s = std::min(s, dimZ);

@@ -497,6 +497,87 @@ static double mean_square(const float* dsi, size_t n_cells)
   return r / (double)n_cells;
 }
 
+// ---------------------------------------------------------------------------------------
+// Depth-map post-processing — MAP:393-436 without the Telea inpainting.
+// OpenCV arithmetic restated (and pinned against cv2 4.13 + the reference's own
+// huangMedianFilter by tests/golden/make_golden_depthmap.py):
+//   conf(0,0) = max_confidence                                                   MAP:396
+//   cv::normalize(conf, conf8, 0, 255, NORM_MINMAX) on CV_32F:                    MAP:397
+//       scale = float(255 / (smax - smin))  (0 when smax - smin <= DBL_EPSILON),
+//       shift = 0.f - float(smin * scale),   dst = src * scale + shift   (float)
+//   conf8(0,0) = 0; convertTo(CV_8U) = saturate(round-half-even)                  MAP:399-400
+//   cv::adaptiveThreshold(conf8, mask, 1, GAUSSIAN_C, THRESH_BINARY, ks, -c):     MAP:405-411
+//       mean = round-half-even(separable [1 2 1]/4, [1 4 6 4 1]/16 or [2 7 14 18 14 7 2]/64
+//       blur, replicated border) — exact integer arithmetic because the sigma=0 kernels of
+//       size <= 7 are dyadic; mask = (conf8 - mean > -ceil(-c)) ? 1 : 0
+//   huangMedianFilter(idx, idx_filtered, mask, median_size)                       MAP:419-423
+//       = for EVERY pixel the lower median of the masked-in indices in the window, 0 if none
+//   removeMaskBoundary(mask, max(ks/2, 1))                                        MAP:426-427
+//   depth = depths[idx_filtered]                                                  MAP:435
+// Returns 0, or -1 for an unsupported kernel size.
+// ---------------------------------------------------------------------------------------
+static int depth_map_post(float* conf, const uint8_t* idx, int rows, int cols, int ks, double c, double max_confidence,
+                          int median_size, const float* depths, uint8_t* conf8_out, uint8_t* mask, uint8_t* idx_filtered,
+                          float* depth)
+{
+  static const int tab3[] = {1, 2, 1}, tab5[] = {1, 4, 6, 4, 1}, tab7[] = {2, 7, 14, 18, 14, 7, 2};
+  const int* tab = ks == 3 ? tab3 : ks == 5 ? tab5 : ks == 7 ? tab7 : nullptr;
+  if (!tab || median_size < 1 || median_size % 2 == 0) return -1;
+  const size_t n = (size_t)rows * cols;
+  conf[0] = (float)max_confidence;
+  float smin = conf[0], smax = conf[0];
+  for (size_t i = 1; i < n; ++i) { smin = std::min(smin, conf[i]); smax = std::max(smax, conf[i]); }
+  const double dscale = 255.0 * (((double)smax - (double)smin) > 2.220446049250313e-16 ? 1.0 / ((double)smax - (double)smin) : 0.0);
+  const float scale = (float)dscale;
+  const float shift = 0.f - (float)((double)smin * (double)scale);
+  std::vector<uint8_t> c8(n);
+  for (size_t i = 0; i < n; ++i) {
+    float v = conf[i] * scale + shift;
+    if (i == 0) v = 0.f;
+    const float r = std::nearbyint(v);   // round-half-even (default rounding mode) == cvRound
+    c8[i] = (uint8_t)(r < 0.f ? 0 : r > 255.f ? 255 : (int)r);   // NaN compares false twice -> (int)NaN; conf is finite here
+  }
+  if (conf8_out) std::memcpy(conf8_out, c8.data(), n);
+  int den = 0;
+  for (int i = 0; i < ks; ++i) den += tab[i];
+  const long long D = (long long)den * den;
+  const int p = ks / 2;
+  const int idelta = (int)std::ceil(-c);
+  auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; };
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      long long acc = 0;
+      for (int i = -p; i <= p; ++i)
+        for (int j = -p; j <= p; ++j)
+          acc += (long long)tab[i + p] * tab[j + p] * c8[(size_t)clampi(y + i, 0, rows - 1) * cols + clampi(x + j, 0, cols - 1)];
+      long long q = acc / D;
+      const long long r = acc % D;
+      if (2 * r > D || (2 * r == D && (q & 1))) ++q;
+      mask[(size_t)y * cols + x] = ((int)c8[(size_t)y * cols + x] - (int)q > -idelta) ? 1 : 0;
+    }
+  const int mp = median_size / 2;
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      int h[256] = {0}, num = 0;
+      for (int i = -mp; i <= mp; ++i)
+        for (int j = -mp; j <= mp; ++j) {
+          const int yy = y + i, xx = x + j;
+          if (yy >= 0 && xx >= 0 && yy < rows && xx < cols && mask[(size_t)yy * cols + xx] > 0) { ++h[idx[(size_t)yy * cols + xx]]; ++num; }
+        }
+      const int middle = (num + 1) / 2;
+      int m = 0, v = 0;
+      for (; v < 256; ++v) { m += h[v]; if (m >= middle) break; }
+      idx_filtered[(size_t)y * cols + x] = (uint8_t)v;
+    }
+  const int border = std::max(ks / 2, 1);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      if (x <= border || x >= cols - border || y <= border || y >= rows - border) mask[(size_t)y * cols + x] = 0;
+      if (depth) depth[(size_t)y * cols + x] = depths[idx_filtered[(size_t)y * cols + x]];
+    }
+  return 0;
+}
+
 }  // namespace oracle
 
 // ---------------------------------------------------------------------------------------
@@ -559,6 +640,10 @@ void oracle_collapse_max(const float* dsi, uint32_t dimX, uint32_t dimY, uint32_
 { oracle::collapse_max(dsi, dimX, dimY, dimZ, depths, conf, idx, depth); }
 
 double oracle_mean_square(const float* dsi, uint64_t n) { return oracle::mean_square(dsi, n); }
+
+int oracle_depth_map_post(float* conf, const uint8_t* idx, int rows, int cols, int ks, double c, double max_confidence,
+                          int median_size, const float* depths, uint8_t* conf8, uint8_t* mask, uint8_t* idx_filtered, float* depth)
+{ return oracle::depth_map_post(conf, idx, rows, cols, ks, c, max_confidence, median_size, depths, conf8, mask, idx_filtered, depth); }
 
 int oracle_num_threads(void)
 {

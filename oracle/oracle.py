@@ -63,6 +63,8 @@ def lib():
         L.oracle_mean_square.argtypes = [vp, u64]
         L.oracle_mean_square.restype = C.c_double
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_depth_map_post.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, vp]
+        L.oracle_depth_map_post.restype = C.c_int
         _lib = L
     return _lib
 
@@ -181,6 +183,22 @@ def collapse_max(dsi, depths=None):
     d = _c(depths, np.float32) if depths is not None else None
     lib().oracle_collapse_max(_p(dsi), dimX, dimY, nz, _p(d), _p(conf), _p(idx), _p(depth))
     return (conf, idx) if depth is None else (conf, idx, depth)
+
+
+def depth_map_post(conf, idx, depths, ks=5, c=5.0, max_confidence=0.0, median_size=5):
+    """getDepthMapFromDSI after the collapse, without inpainting (mapper_emvs_stereo.cpp:393-436).
+    -> dict(conf [with conf(0,0) = max_confidence, as the reference leaves it], conf8, mask, idx_filtered, depth)"""
+    conf = np.array(conf, np.float32, copy=True, order="C")
+    idx = _c(idx, np.uint8)
+    rows, cols = conf.shape
+    depths = _c(depths, np.float32)
+    out = dict(conf=conf, conf8=np.zeros((rows, cols), np.uint8), mask=np.zeros((rows, cols), np.uint8),
+               idx_filtered=np.zeros((rows, cols), np.uint8), depth=np.zeros((rows, cols), np.float32))
+    rc = lib().oracle_depth_map_post(_p(conf), _p(idx), rows, cols, int(ks), float(c), float(max_confidence), int(median_size),
+                                     _p(depths), _p(out["conf8"]), _p(out["mask"]), _p(out["idx_filtered"]), _p(out["depth"]))
+    if rc != 0:
+        raise ValueError("unsupported adaptive_threshold_kernel_size / median_filter_size")
+    return out
 
 
 def mean_square(dsi):

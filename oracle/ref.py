@@ -40,6 +40,7 @@ def lib():
         L.ref_mean_square.argtypes = [u32, u32, u32, vp]
         L.ref_mean_square.restype = C.c_double
         L.ref_depth_vector.argtypes = [C.c_int, f32, f32, u64, vp]
+        L.ref_huang_median.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -84,4 +85,12 @@ def mean_square(vol):
 def depth_vector(zmin, zmax, nz, inverse=False):
     out = np.zeros(nz, np.float32)
     lib().ref_depth_vector(int(inverse), zmin, zmax, nz, _p(out))
+    return out
+
+
+def huang_median(img, mask, patch_size):
+    """The reference's huangMedianFilter (median_filtering.cpp:33-158) on uint8 images."""
+    img, mask = np.ascontiguousarray(img, np.uint8), np.ascontiguousarray(mask, np.uint8)
+    out = np.zeros_like(img)
+    lib().ref_huang_median(_p(img), _p(mask), img.shape[0], img.shape[1], int(patch_size), _p(out))
     return out

@@ -4,6 +4,7 @@
 // (oracle/shim/emvs_cv_shim.h); every float operation executed here is the reference's.
 #include <cartesian3dgrid/cartesian3dgrid.h>
 #include <mapper_emvs_stereo/depth_vector.hpp>
+#include <mapper_emvs_stereo/median_filtering.hpp>
 
 #include <cstdint>
 #include <cstring>
@@ -58,8 +59,8 @@ void ref_collapse_max(uint32_t dimX, uint32_t dimY, uint32_t dimZ, const float* 
   load(g, vol, (size_t)dimX * dimY * dimZ);
   cv::Mat mv, mi;
   g.collapseMaxZSlice(&mv, &mi);
-  std::memcpy(conf, mv.data(), (size_t)dimX * dimY * sizeof(float));
-  std::memcpy(idx, mi.data(), (size_t)dimX * dimY);
+  std::memcpy(conf, mv.data, (size_t)dimX * dimY * sizeof(float));
+  std::memcpy(idx, mi.data, (size_t)dimX * dimY);
 }
 
 // raw_depths_vec_ as MapperEMVS::setupDSI builds it (mapper_emvs_stereo.cpp:213-214) from the
@@ -70,6 +71,15 @@ void ref_depth_vector(int inverse, float zmin, float zmax, uint64_t nz, float* o
   if (inverse) v = EMVS::InverseDepthVector(zmin, zmax, (size_t)nz).getDepthVector();
   else v = EMVS::LinearDepthVector(zmin, zmax, (size_t)nz).getDepthVector();
   std::memcpy(out, v.data(), v.size() * sizeof(float));
+}
+
+// huangMedianFilter(img, out, mask, patch_size) — mapper_emvs_stereo/src/median_filtering.cpp:33-158
+// (the masked median that cleans the depth-cell indices, mapper_emvs_stereo.cpp:418-423).
+void ref_huang_median(const uint8_t* img, const uint8_t* mask, int rows, int cols, int patch_size, uint8_t* out)
+{
+  cv::Mat mi(rows, cols, CV_8U, (void*)img), mm(rows, cols, CV_8U, (void*)mask), mo;
+  huangMedianFilter(mi, mo, mm, patch_size);
+  std::memcpy(out, mo.data, (size_t)rows * cols);
 }
 
 // Grid3D::computeMeanSquare.  cartesian3dgrid.cpp:164-174

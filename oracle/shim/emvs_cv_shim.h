@@ -3,7 +3,8 @@
 // and its header compile IN PLACE into oracle/_ref/libgrid3d_ref.so (see oracle/Makefile, target ref).
 //
 // TEST INFRASTRUCTURE ONLY.  cv::Mat here is a dense row-major 2-D buffer with the handful of
-// members the Grid3D hot path touches (constructor, at<T>, rows, cols).  Everything that only
+// members the Grid3D hot path and huangMedianFilter touch (constructor, at<T>, rows, cols, data,
+// type, clone).  Everything that only
 // the reference's unused focus-collapse methods call (Sobel, GaussianBlur, Mat arithmetic, ...)
 // is declared so those methods type-check, and aborts if it is ever executed: nothing on the
 // mapping hot path reaches it (cartesian3dgrid.cpp:192-483 are never called with method = -1,
@@ -43,20 +44,27 @@ enum { BORDER_REFLECT = 2, THRESH_TOZERO = 3 };
 class Mat {
  public:
   int rows = 0, cols = 0;
+  unsigned char* data = nullptr;
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
-  Mat(int r, int c, int type, void* ext) : rows(r), cols(c), type_(type), ext_((unsigned char*)ext) {}
+  Mat(int r, int c, int type, void* ext) : rows(r), cols(c), data((unsigned char*)ext), type_(type) {}
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }  // create() zero-fills
   void create(int r, int c, int type)
   {
-    rows = r; cols = c; type_ = type; ext_ = nullptr;
-    own_ = std::make_shared<std::vector<unsigned char>>((size_t)r * c * elem(), (unsigned char)0);
+    rows = r; cols = c; type_ = type;
+    own_ = std::make_shared<std::vector<unsigned char>>((size_t)r * c * elem() + 1, (unsigned char)0);
+    data = own_->data();
   }
-  template <typename T> T& at(int y, int x) { return reinterpret_cast<T*>(data())[(size_t)y * cols + x]; }
-  template <typename T> const T& at(int y, int x) const { return reinterpret_cast<const T*>(data())[(size_t)y * cols + x]; }
-  unsigned char* data() { return ext_ ? ext_ : own_->data(); }
-  const unsigned char* data() const { return ext_ ? ext_ : own_->data(); }
+  template <typename T> T& at(int y, int x) { return reinterpret_cast<T*>(data)[(size_t)y * cols + x]; }
+  template <typename T> const T& at(int y, int x) const { return reinterpret_cast<const T*>(data)[(size_t)y * cols + x]; }
   size_t elem() const { return type_ == CV_8U ? 1 : 4; }
+  int type() const { return type_; }
+  Mat clone() const
+  {
+    Mat m(rows, cols, type_);
+    if (data) std::memcpy(m.data, data, (size_t)rows * cols * elem());
+    return m;
+  }
   // members used only by the reference's unused focus collapses
   Mat mul(const Mat&) const { shim_unreachable("Mat::mul"); }
   Mat t() const { shim_unreachable("Mat::t"); }
@@ -65,7 +73,6 @@ class Mat {
 
  private:
   int type_ = CV_32F;
-  unsigned char* ext_ = nullptr;
   std::shared_ptr<std::vector<unsigned char>> own_;
 };
 
