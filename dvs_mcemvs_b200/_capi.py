@@ -43,6 +43,11 @@ class Camera(C.Structure):
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
 
 
+class DepthMapOptions(C.Structure):
+    _fields_ = [("adaptive_threshold_kernel_size", C.c_int32), ("adaptive_threshold_c", C.c_double),
+                ("max_confidence", C.c_double), ("median_filter_size", C.c_int32)]
+
+
 class EmvsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"emvs error {code}: {msg}")
@@ -87,6 +92,9 @@ _PROTOTYPES = {
     "emvs_grid_collapse_max": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "emvs_fuse_collapse": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "emvs_fuse_collapse_device": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "emvs_depth_map_from_dsi": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, C.POINTER(DepthMapOptions), _vp, _vp, _vp, _vp]),
+    "emvs_depth_map_postprocess": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32,
+                                             C.POINTER(DepthMapOptions), _vp, _vp, _vp, _vp, _vp]),
     "emvs_grid_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
     "emvs_mapper_create": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(Shape), C.POINTER(_vp)]),
     "emvs_mapper_destroy": (C.c_int, [_vp]),

@@ -308,6 +308,54 @@ def fuse_collapse_device(grids, method, d_depths, d_conf, d_idx, d_depth, fused_
                                            C.c_void_p(d_idx), C.c_void_p(d_depth) if d_depth else None))
 
 
+class OptionsDepthMap:
+    """The fields of EMVS::OptionsDepthMap (mapper_emvs_stereo.hpp:68-82) that getDepthMapFromDSI reads;
+    defaults of main.cpp:73-75,97."""
+
+    def __init__(self, adaptive_threshold_kernel_size=5, adaptive_threshold_c=5.0, median_filter_size=5, max_confidence=0.0):
+        self.adaptive_threshold_kernel_size_ = int(adaptive_threshold_kernel_size)
+        self.adaptive_threshold_c_ = float(adaptive_threshold_c)
+        self.median_filter_size_ = int(median_filter_size)
+        self.max_confidence = float(max_confidence)
+
+    def c_struct(self):
+        return capi.DepthMapOptions(self.adaptive_threshold_kernel_size_, self.adaptive_threshold_c_, self.max_confidence,
+                                    self.median_filter_size_)
+
+
+def depth_map_from_dsi(grids, method, depths, options):
+    """getDepthMapFromDSI for method = -1 without the inpainting (mapper_emvs_stereo.cpp:339-436) on the fusion of
+    `grids` (one grid: no fusion) -> (depth_map, confidence_map, mask, depth_cell_indices_filtered)."""
+    g0 = grids[0]
+    dimX, dimY, dimZ = g0.size_
+    arr = (C.c_void_p * len(grids))(*[g._h for g in grids])
+    depth = np.empty((dimY, dimX), np.float32)
+    conf = np.empty((dimY, dimX), np.float32)
+    mask = np.empty((dimY, dimX), np.uint8)
+    idx_f = np.empty((dimY, dimX), np.uint8)
+    d = np.ascontiguousarray(depths, np.float32)
+    opt = options.c_struct()
+    check(_lib().emvs_depth_map_from_dsi(arr, len(grids), int(method), ptr(d), C.byref(opt), ptr(depth), ptr(conf), ptr(mask),
+                                         ptr(idx_f)))
+    return depth, conf, mask, idx_f
+
+
+def depth_map_postprocess(ctx, conf, idx, depths, ks=5, c=5.0, max_confidence=0.0, median_size=5):
+    """The post-processing alone on host maps -> dict(conf, conf8, mask, idx_filtered, depth)."""
+    conf = np.ascontiguousarray(conf, np.float32)
+    idx = np.ascontiguousarray(idx, np.uint8)
+    rows, cols = conf.shape
+    d = np.ascontiguousarray(depths, np.float32)
+    out = dict(conf=np.empty((rows, cols), np.float32), conf8=np.empty((rows, cols), np.uint8),
+               mask=np.empty((rows, cols), np.uint8), idx_filtered=np.empty((rows, cols), np.uint8),
+               depth=np.empty((rows, cols), np.float32))
+    opt = capi.DepthMapOptions(int(ks), float(c), float(max_confidence), int(median_size))
+    check(_lib().emvs_depth_map_postprocess(ctx._h, ptr(conf), ptr(idx), rows, cols, ptr(d), d.shape[0], C.byref(opt),
+                                            ptr(out["depth"]), ptr(out["conf"]), ptr(out["mask"]), ptr(out["idx_filtered"]),
+                                            ptr(out["conf8"])))
+    return out
+
+
 class PeerExchange:
     """Fused multi-GPU reduce + fuse + argmax over NVLink peer memory (emvs_exchange_*).
 
@@ -438,9 +486,13 @@ class MapperEMVS:
     def counts_allreduce(self):
         check(_lib().emvs_mapper_counts_allreduce(self._h))
 
-    def getDepthMapFromDSI(self):
-        """Hot part of getDepthMapFromDSI (mapper_emvs_stereo.cpp:344-375 + :302-313, method=-1):
-        -> (depth_map, confidence_map, depth_cell_indices) with depth = depths[raw argmax]."""
+    def getDepthMapFromDSI(self, options_depth_map=None):
+        """Without options: the hot part of getDepthMapFromDSI (mapper_emvs_stereo.cpp:344-375 + :302-313,
+        method=-1) -> (depth_map, confidence_map, depth_cell_indices) with depth = depths[raw argmax].
+        With an OptionsDepthMap: the whole function minus the inpainting (:339-436)
+        -> (depth_map, confidence_map, mask, depth_cell_indices_filtered)."""
+        if options_depth_map is not None:
+            return depth_map_from_dsi([self.dsi_], 6, self.raw_depths_vec_, options_depth_map)
         conf, idx, depth = self.dsi_.collapseMaxZSlice(self.raw_depths_vec_)
         return depth, conf, idx
 

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -848,6 +849,135 @@ int emvs_fuse_collapse_device(emvs_grid* const* grids, int n, int method, const 
   DeviceGuard guard(g->ctx->device);
   return launch_fuse_collapse(g->ctx, A, g->dimX * g->dimY, g->dimZ, d_depths, fused_out ? fused_out->d : nullptr,
                               d_conf, d_idx, g->dimZ <= 256 ? 1 : 2, d_depth);
+}
+
+// ---- depth-map post-processing ------------------------------------------------------------------
+static int check_post_options(const emvs_depthmap_options* o)
+{
+  REQUIRE(o, EMVS_ERR_INVALID, "depth map options are NULL");
+  REQUIRE(o->adaptive_threshold_kernel_size == 3 || o->adaptive_threshold_kernel_size == 5 ||
+              o->adaptive_threshold_kernel_size == 7,
+          EMVS_ERR_INVALID, "adaptive_threshold_kernel_size must be 3, 5 or 7 (the dyadic sigma=0 Gaussian kernels)");
+  REQUIRE(o->median_filter_size >= 1 && (o->median_filter_size % 2) == 1, EMVS_ERR_INVALID,
+          "median_filter_size must be odd");   // CHECK_EQ(patch_size % 2, 1), median_filtering.cpp:43
+  return EMVS_OK;
+}
+
+// Device buffers inside ctx->d_out, laid out by post_layout(); conf and idx are already there.
+struct PostBuffers {
+  float* conf; float* depth; uint8_t* idx; uint8_t* conf8; uint8_t* mask; uint8_t* idx_f; float* tab;
+  float2* partial; PostScale* scale;
+  size_t total;
+};
+
+static PostBuffers post_layout(char* base, size_t n_pix, size_t n_depths)
+{
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  PostBuffers b;
+  size_t o = 0;
+  b.conf = (float*)(base + o); o = up(o + n_pix * 4);
+  b.depth = (float*)(base + o); o = up(o + n_pix * 4);
+  b.idx = (uint8_t*)(base + o); o = up(o + n_pix * 2);
+  b.conf8 = (uint8_t*)(base + o); o = up(o + n_pix);
+  b.mask = (uint8_t*)(base + o); o = up(o + n_pix);
+  b.idx_f = (uint8_t*)(base + o); o = up(o + n_pix);
+  b.tab = (float*)(base + o); o = up(o + n_depths * 4);
+  b.partial = (float2*)(base + o); o = up(o + 256 * sizeof(float2));
+  b.scale = (PostScale*)(base + o); o = up(o + sizeof(PostScale));
+  b.total = o;
+  return b;
+}
+
+static int run_post(emvs_context* ctx, const PostBuffers& b, uint32_t rows, uint32_t cols, const emvs_depthmap_options* opt)
+{
+  cudaStream_t st = ctx->stream;
+  const uint32_t n_pix = rows * cols;
+  const int nb = (int)std::min<uint32_t>((n_pix + 255) / 256, 256);
+  k_post_minmax<<<nb, 256, 0, st>>>(b.conf, n_pix, (float)opt->max_confidence, b.partial);
+  k_post_minmax_final<<<1, 256, 0, st>>>(b.partial, nb, b.scale);
+  k_post_to_u8<<<(n_pix + 255) / 256, 256, 0, st>>>(b.conf, n_pix, b.scale, b.conf8);
+  const dim3 tb(32, 8), tg((cols + 31) / 32, (rows + 7) / 8);
+  const int idelta = (int)std::ceil(-opt->adaptive_threshold_c);   // cvCeil(delta) with delta = -c (THRESH_BINARY)
+  switch (opt->adaptive_threshold_kernel_size) {
+    case 3: k_post_adaptive_threshold<3><<<tg, tb, 0, st>>>(b.conf8, (int)rows, (int)cols, idelta, b.mask); break;
+    case 5: k_post_adaptive_threshold<5><<<tg, tb, 0, st>>>(b.conf8, (int)rows, (int)cols, idelta, b.mask); break;
+    default: k_post_adaptive_threshold<7><<<tg, tb, 0, st>>>(b.conf8, (int)rows, (int)cols, idelta, b.mask); break;
+  }
+  k_post_masked_median<<<tg, tb, 0, st>>>(b.idx, b.mask, (int)rows, (int)cols, opt->median_filter_size / 2, b.idx_f);
+  const int border = std::max(opt->adaptive_threshold_kernel_size / 2, 1);
+  k_post_finalize<<<tg, tb, 0, st>>>(b.mask, b.idx_f, (int)rows, (int)cols, border, b.tab, b.depth);
+  ctx->launches += 6;
+  CUDA_TRY(cudaGetLastError());
+  return EMVS_OK;
+}
+
+static int post_download(emvs_context* ctx, const PostBuffers& b, size_t n_pix, float* depth_map, float* confidence_map,
+                         uint8_t* mask, uint8_t* idx_filtered, uint8_t* conf8)
+{
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(cudaMemcpyAsync(depth_map, b.depth, n_pix * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(confidence_map, b.conf, n_pix * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(mask, b.mask, n_pix, cudaMemcpyDeviceToHost, st));
+  if (idx_filtered) CUDA_TRY(cudaMemcpyAsync(idx_filtered, b.idx_f, n_pix, cudaMemcpyDeviceToHost, st));
+  if (conf8) CUDA_TRY(cudaMemcpyAsync(conf8, b.conf8, n_pix, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return EMVS_OK;
+}
+
+int emvs_depth_map_from_dsi(emvs_grid* const* grids, int n, int method, const float* depths,
+                            const emvs_depthmap_options* opt, float* depth_map, float* confidence_map, uint8_t* mask,
+                            uint8_t* idx_filtered)
+{
+  REQUIRE(grids && n >= 1 && n <= kMaxFuse, EMVS_ERR_INVALID, "depth_map_from_dsi: need 1..8 grids");
+  REQUIRE(n == 1 || (method >= EMVS_FUSE_MIN && method <= EMVS_FUSE_MAX), EMVS_ERR_INVALID, "Improper fusion method selected");
+  REQUIRE(depths && depth_map && confidence_map && mask, EMVS_ERR_INVALID, "depth_map_from_dsi: NULL argument");
+  int rc = check_post_options(opt);
+  if (rc) return rc;
+  FuseArgs A{};
+  A.n = n;
+  A.method = n == 1 ? EMVS_FUSE_MAX : method;
+  for (int i = 0; i < n; ++i) {
+    REQUIRE(grids[i], EMVS_ERR_INVALID, "depth_map_from_dsi: NULL grid");
+    REQUIRE(same_dims(grids[0], grids[i]), EMVS_ERR_INVALID, "depth_map_from_dsi: grids differ in shape or context");
+    A.g[i] = grids[i]->d;
+  }
+  const emvs_grid* g = grids[0];
+  REQUIRE(g->dimZ <= 256, EMVS_ERR_INVALID, "depth_map_from_dsi: dimZ > 256 (8-bit depth indices, main.cpp:156)");
+  emvs_context* ctx = g->ctx;
+  DeviceGuard guard(ctx->device);
+  const size_t n_pix = (size_t)g->dimX * g->dimY;
+  const size_t need = post_layout(nullptr, n_pix, g->dimZ).total;
+  rc = grow(&ctx->d_out, &ctx->out_cap, need);
+  if (rc) return rc;
+  const PostBuffers b = post_layout((char*)ctx->d_out, n_pix, g->dimZ);
+  CUDA_TRY(cudaMemcpyAsync(b.tab, depths, (size_t)g->dimZ * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_fuse_collapse(ctx, A, (uint32_t)n_pix, g->dimZ, b.tab, nullptr, b.conf, b.idx, 1, nullptr);
+  if (rc) return rc;
+  rc = run_post(ctx, b, g->dimY, g->dimX, opt);
+  if (rc) return rc;
+  return post_download(ctx, b, n_pix, depth_map, confidence_map, mask, idx_filtered, nullptr);
+}
+
+int emvs_depth_map_postprocess(emvs_context* ctx, const float* conf_in, const uint8_t* idx_in, uint32_t rows, uint32_t cols,
+                               const float* depths, uint32_t n_depths, const emvs_depthmap_options* opt, float* depth_map,
+                               float* confidence_map, uint8_t* mask, uint8_t* idx_filtered, uint8_t* conf8)
+{
+  REQUIRE(ctx && conf_in && idx_in && depths && depth_map && confidence_map && mask, EMVS_ERR_INVALID,
+          "depth_map_postprocess: NULL argument");
+  REQUIRE(rows && cols && n_depths >= 1 && n_depths <= 256, EMVS_ERR_INVALID, "depth_map_postprocess: bad size");
+  int rc = check_post_options(opt);
+  if (rc) return rc;
+  DeviceGuard guard(ctx->device);
+  const size_t n_pix = (size_t)rows * cols;
+  rc = grow(&ctx->d_out, &ctx->out_cap, post_layout(nullptr, n_pix, n_depths).total);
+  if (rc) return rc;
+  const PostBuffers b = post_layout((char*)ctx->d_out, n_pix, n_depths);
+  CUDA_TRY(cudaMemcpyAsync(b.tab, depths, (size_t)n_depths * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(b.conf, conf_in, n_pix * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(b.idx, idx_in, n_pix, cudaMemcpyHostToDevice, ctx->stream));
+  rc = run_post(ctx, b, rows, cols, opt);
+  if (rc) return rc;
+  return post_download(ctx, b, n_pix, depth_map, confidence_map, mask, idx_filtered, conf8);
 }
 
 int emvs_grid_device_ptr(const emvs_grid* g, void** out)

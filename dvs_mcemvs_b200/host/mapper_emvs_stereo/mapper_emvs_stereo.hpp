@@ -114,6 +114,19 @@ struct ShapeDSI {
   float fov_ = 0;
 };
 
+// mapper_emvs_stereo.hpp:68-82 (the members getDepthMapFromDSI reads; the rest is I/O bookkeeping of main.cpp)
+struct OptionsDepthMap {
+  int adaptive_threshold_kernel_size_ = 5;
+  double adaptive_threshold_c_ = 5.;
+  double max_confidence = 0.;
+  bool full_sequence = false;
+  bool save_conf_stats = false;
+  bool save_mono = false;
+  bool save_dsi = false;
+  double rv_pos = 0.;
+  int median_filter_size_ = 5;
+};
+
 typedef LinearTrajectory TrajectoryType;
 
 class MapperEMVS {
@@ -188,6 +201,29 @@ class MapperEMVS {
     depth_cell_indices.create(rows, cols);
     emvs_host::check(emvs_grid_collapse_max(dsi_.handle(), raw_depths_vec_.data(), confidence_map.data.data(),
                                             depth_cell_indices.data.data(), depth_map.data.data()),
+                     "getDepthMapFromDSI");
+  }
+
+  // getDepthMapFromDSI(depth_map, confidence_map, mask, options_depth_map) for method = -1
+  // (mapper_emvs_stereo.cpp:339-436) without the Telea inpainting: the depth map is the depth of the
+  // median-filtered indices, the mask is the adaptive-threshold mask with its border removed, and
+  // confidence_map(0,0) is overwritten with max_confidence exactly like the reference leaves it.
+  // The dense (inpainted) map stays with the caller's cv::inpaint on depth_cell_indices_filtered.
+  void getDepthMapFromDSI(emvs_host::Image<float>& depth_map, emvs_host::Image<float>& confidence_map,
+                          emvs_host::Image<uint8_t>& mask, const OptionsDepthMap& options_depth_map,
+                          emvs_host::Image<uint8_t>* depth_cell_indices_filtered = nullptr)
+  {
+    const int rows = (int)dsi_shape_.dimY_, cols = (int)dsi_shape_.dimX_;
+    depth_map.create(rows, cols);
+    confidence_map.create(rows, cols);
+    mask.create(rows, cols);
+    if (depth_cell_indices_filtered) depth_cell_indices_filtered->create(rows, cols);
+    emvs_depthmap_options o{options_depth_map.adaptive_threshold_kernel_size_, options_depth_map.adaptive_threshold_c_,
+                            options_depth_map.max_confidence, options_depth_map.median_filter_size_};
+    emvs_grid* g = dsi_.handle();
+    emvs_host::check(emvs_depth_map_from_dsi(&g, 1, EMVS_FUSE_MAX, raw_depths_vec_.data(), &o, depth_map.data.data(),
+                                             confidence_map.data.data(), mask.data.data(),
+                                             depth_cell_indices_filtered ? depth_cell_indices_filtered->data.data() : nullptr),
                      "getDepthMapFromDSI");
   }
 

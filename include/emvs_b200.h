@@ -222,6 +222,28 @@ EMVS_API int emvs_fuse_collapse(emvs_grid* const* grids, int n, int method, cons
  * asynchronous on the context's stream: nothing is copied to the host (bench `value`). */
 EMVS_API int emvs_fuse_collapse_device(emvs_grid* const* grids, int n, int method, const float* d_depths,
                               emvs_grid* fused_out, float* d_conf, void* d_idx, float* d_depth);
+/* Options of MapperEMVS::getDepthMapFromDSI that the device post-processing reads
+ * (OptionsDepthMap, MHP:68-82; defaults of main.cpp:73-75,97). */
+typedef struct emvs_depthmap_options {
+  int32_t adaptive_threshold_kernel_size;  /* 3, 5 or 7 (every shipped .conf uses the default 5)  */
+  double adaptive_threshold_c;
+  double max_confidence;                   /* 0: the reference's default                           */
+  int32_t median_filter_size;              /* odd, >= 1                                            */
+} emvs_depthmap_options;
+/* MapperEMVS::getDepthMapFromDSI (MAP:339-436) for method = -1 WITHOUT the Telea inpainting:
+ * n-ary fusion (n == 1: none) + collapseMaxZSlice, conf(0,0) = max_confidence, min-max
+ * normalisation to 8 bit, adaptive Gaussian threshold -> mask, masked Huang median of the depth
+ * indices, border removal, depth = depths[filtered index].  Host outputs, dimY*dimX each:
+ * depth_map f32, confidence_map f32 (with (0,0) overwritten like the reference leaves it),
+ * mask u8 (0/1), idx_filtered u8 (may be NULL).  dimZ must be <= 256 (the reference's limit). */
+EMVS_API int emvs_depth_map_from_dsi(emvs_grid* const* grids, int n, int method, const float* depths,
+                            const emvs_depthmap_options* opt, float* depth_map, float* confidence_map,
+                            uint8_t* mask, uint8_t* idx_filtered);
+/* The post-processing alone on HOST confidence / index maps (rows x cols), same outputs. */
+EMVS_API int emvs_depth_map_postprocess(emvs_context* ctx, const float* conf_in, const uint8_t* idx_in, uint32_t rows,
+                               uint32_t cols, const float* depths, uint32_t n_depths, const emvs_depthmap_options* opt,
+                               float* depth_map, float* confidence_map, uint8_t* mask, uint8_t* idx_filtered,
+                               uint8_t* conf8 /* may be NULL */);
 /* Raw device pointer of the volume (for collectives run by the caller, e.g. torch.distributed). */
 EMVS_API int emvs_grid_device_ptr(const emvs_grid* g, void** out);
 
