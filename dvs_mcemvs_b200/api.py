@@ -516,3 +516,78 @@ def process_1(mappers, events, trajectories, T_rv_w, fusion_method, mapper_fused
     conf, idx, depth = fuse_collapse(grids, fusion_method, mappers[0].raw_depths_vec_,
                                      mapper_fused.dsi_ if mapper_fused is not None else None)
     return depth, conf, idx
+
+
+# --------------------------------------------------------------------------------------------
+# process_2 / process_5 (Alg. 2: fusion across cameras and time) — process2.cpp:28-302,
+# process5.cpp:27-260, compute steps only
+# --------------------------------------------------------------------------------------------
+_PAIR_METHOD = {1: "minTwoGrids", 2: "harmonicMeanTwoGrids", 3: "geometricMeanTwoGrids", 4: "arithmeticMeanTwoGrids",
+                5: "rmsTwoGrids", 6: "maxTwoGrids"}
+
+
+def subinterval_slices(n_events, num_subintervals, shift=0):
+    """Event ranges of the sub-intervals: split BY COUNT (process2.cpp:46-47, 105-107), the remainder
+    n_events % num_subintervals is dropped.  shift > 0 (process_5, process5.cpp:89-150): start at
+    sub-interval `shift` and wrap around the end of the stream.  -> list of (list of (lo, hi))."""
+    per = n_events // num_subintervals
+    out, first = [], shift * per
+    for _ in range(num_subintervals):
+        if shift and first + per >= n_events:                 # process5.cpp:136-143
+            out.append([(first, n_events), (0, first + per - n_events)])
+            first = first + per - n_events
+        else:
+            out.append([(first, first + per)])
+            first += per
+    return out
+
+
+def process_2(ctx, cams, trajectories, events, dsi_shape, num_subintervals, T_rv_w, stereo_fusion, temporal_fusion,
+              shuffle=False, replicate_camera_time_id_swap=False):
+    """Alg. 2 on two cameras.  Per sub-interval k: evaluateDSI left / right, stereo-fuse, accumulate over
+    time (temporal_fusion 2 = HM: sum of 1/(0.01+x) then n/sum; 4 = AM: sum then /n; any other id
+    accumulates nothing, like the reference's empty switch cases).  Returns the four volumes the reference
+    produces: dict(fused [camera then time], left, right [time per camera], camera_time [time then camera]).
+
+    shuffle=True is process_5: the right camera starts at sub-interval n/2 and wraps around.
+    The reference's time-then-camera switch maps ids 3 -> AM and 4 -> GM, swapped relative to every other
+    place (process2.cpp:274-279); that is replicated only on request."""
+    if stereo_fusion not in _PAIR_METHOD:
+        raise ValueError("Improper fusion method selected")
+    cam0, cam1 = cams
+    mapper0, mapper1 = MapperEMVS(ctx, cam0, dsi_shape), MapperEMVS(ctx, cam1, dsi_shape)
+    dimX, dimY, dimZ = mapper0.dsi_.size_
+    fused_sub, fused, left, right, camera_time = (Grid3D(ctx, dimX, dimY, dimZ) for _ in range(5))
+    ev = [np.ascontiguousarray(e, dtype=EVENT_DTYPE) for e in events]
+    sl0 = subinterval_slices(len(ev[0]), num_subintervals)
+    sl1 = subinterval_slices(len(ev[1]), num_subintervals, num_subintervals // 2 if shuffle else 0)
+    for k in range(num_subintervals):
+        for m, e, sl, tr in ((mapper0, ev[0], sl0[k], trajectories[0]), (mapper1, ev[1], sl1[k], trajectories[1])):
+            subset = np.concatenate([e[lo:hi] for lo, hi in sl]) if len(sl) > 1 else e[sl[0][0]:sl[0][1]]
+            if not m.evaluateDSI(subset, tr, T_rv_w):
+                m.dsi_.resetGrid()      # the reference resets both DSIs at the top of every iteration (process2.cpp:100-101)
+        fused_sub.copyFrom(mapper0.dsi_)                                   # resetGrid + addTwoGrids (process2.cpp:159-160)
+        getattr(fused_sub, _PAIR_METHOD[stereo_fusion])(mapper1.dsi_)
+        if temporal_fusion == 2:
+            left.addInverseOfTwoGrids(mapper0.dsi_)
+            right.addInverseOfTwoGrids(mapper1.dsi_)
+            fused.addInverseOfTwoGrids(fused_sub)
+        elif temporal_fusion == 4:
+            left.addTwoGrids(mapper0.dsi_)
+            right.addTwoGrids(mapper1.dsi_)
+            fused.addTwoGrids(fused_sub)
+    if temporal_fusion == 2:
+        for g in (left, right, fused):
+            g.computeHMfromSumOfInv(num_subintervals)
+    elif temporal_fusion == 4:
+        for g in (left, right, fused):
+            g.computeAMfromSum(num_subintervals)
+    camera_time.addTwoGrids(left)                                          # process2.cpp:267
+    m = stereo_fusion
+    if replicate_camera_time_id_swap and m in (3, 4):
+        m = 7 - m
+    getattr(camera_time, _PAIR_METHOD[m])(right)
+    mapper0.close()
+    mapper1.close()
+    fused_sub.close()
+    return dict(fused=fused, left=left, right=right, camera_time=camera_time)
