@@ -21,6 +21,7 @@ FUSE_MIN, FUSE_HM, FUSE_GM, FUSE_AM, FUSE_RMS, FUSE_MAX = 1, 2, 3, 4, 5, 6
 (OP_ADD, OP_MIN, OP_HM, OP_GM, OP_AM, OP_RMS, OP_MAX, OP_HM_N, OP_ADD_INV, OP_HM_FROM_SUMINV,
  OP_AM_FROM_SUM) = range(11)
 BUILD_RESET, BUILD_ACCUMULATE, BUILD_ALLREDUCE = 0, 1, 2
+DISTORTION_NONE, DISTORTION_PLUMB_BOB, DISTORTION_FISHEYE = 0, 1, 2
 
 # numpy views of the POD structs (layouts asserted against the C side in tests/test_abi.py)
 EVENT_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("sec", "<u4"), ("nsec", "<u4"),
@@ -75,6 +76,7 @@ _PROTOTYPES = {
     "emvs_host_free": (C.c_int, [_vp]),
     "emvs_depth_vector": (C.c_int, [C.POINTER(Shape), _vp]),
     "emvs_virtual_camera": (C.c_int, [C.POINTER(Camera), C.POINTER(Shape), _vp]),
+    "emvs_rectify_lut": (C.c_int, [C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "emvs_trajectory_pose_at": (C.c_int, [_vp, _sz, C.c_uint32, C.c_uint32, _vp, C.POINTER(C.c_int)]),
     "emvs_pose_compose": (C.c_int, [_vp, _vp, _vp]),
     "emvs_pose_inverse": (C.c_int, [_vp, _vp]),

@@ -57,6 +57,20 @@ class CameraModel:
     def c_struct(self):
         return Camera(self.width, self.height, self.fx, self.fy, self.cx, self.cy)
 
+    @classmethod
+    def from_camera_info(cls, width, height, K, D, R, P, distortion_model):
+        """What MapperEMVS derives from a sensor_msgs/CameraInfo-backed PinholeCameraModel: projection-matrix
+        intrinsics (mapper_emvs_stereo.cpp:46-48) and the LUT of precomputeRectifiedPoints (:256-299).
+        distortion_model: "plumb_bob" or "fisheye" (anything else raises, like the reference's LOG(ERROR))."""
+        model = {"plumb_bob": capi.DISTORTION_PLUMB_BOB, "fisheye": capi.DISTORTION_FISHEYE}.get(distortion_model, -1)
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        R = np.ascontiguousarray(R, np.float64).reshape(9)
+        P = np.ascontiguousarray(P, np.float64).reshape(12)
+        D = np.ascontiguousarray(D, np.float64).reshape(-1)
+        lut = np.empty((int(height) * int(width), 2), np.float32)
+        check(_lib().emvs_rectify_lut(model, ptr(K), ptr(D), D.shape[0], ptr(R), ptr(P), int(width), int(height), ptr(lut)))
+        return cls(width, height, P[0], P[5], P[2], P[6], lut=lut)
+
 
 def make_pose(q=(1.0, 0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0)):
     p = np.zeros((), dtype=POSE_DTYPE)

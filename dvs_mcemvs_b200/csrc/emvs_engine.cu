@@ -642,6 +642,16 @@ int emvs_virtual_camera(const emvs_camera* cam, const emvs_shape* shape, float o
   return EMVS_OK;
 }
 
+int emvs_rectify_lut(int model, const double K[9], const double* D, int n_d, const double R[9], const double P[12],
+                     uint32_t width, uint32_t height, float* out)
+{
+  REQUIRE(K && R && P && out && (D || n_d == 0), EMVS_ERR_INVALID, "rectify_lut: NULL argument");
+  REQUIRE(width && height && n_d >= 0 && n_d <= 14, EMVS_ERR_INVALID, "rectify_lut: bad size");
+  REQUIRE(host_rectify_lut(model, K, D, n_d, R, P, width, height, out) == 0, EMVS_ERR_INVALID,
+          "Distortion model not set properly!");   // MAP:293
+  return EMVS_OK;
+}
+
 int emvs_trajectory_pose_at(const emvs_stamped_pose* traj, size_t n, uint32_t sec, uint32_t nsec, emvs_pose* out,
                             int* found)
 {

@@ -18,6 +18,8 @@ void host_virtual_camera(const emvs_camera& cam, const emvs_shape& shape, float 
 bool host_pose_at(const emvs_stamped_pose* traj, size_t n, uint32_t sec, uint32_t nsec, emvs_pose* out);
 void host_pose_compose(const emvs_pose& a, const emvs_pose& b, emvs_pose* out);
 void host_pose_inverse(const emvs_pose& a, emvs_pose* out);
+int host_rectify_lut(int model, const double K[9], const double* D, int n_d, const double R[9], const double P[12],
+                     uint32_t W, uint32_t H, float* out);
 size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
                       const emvs_pose& T_rv_w, const emvs_camera& cam, const float virt[4], float z0,
                       emvs_packet* out, size_t max_out);

@@ -16,6 +16,7 @@
 
 #include "emvs_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -221,6 +222,93 @@ bool host_pose_at(const emvs_stamped_pose* traj, size_t n, uint32_t sec, uint32_
 
 void host_pose_compose(const emvs_pose& a, const emvs_pose& b, emvs_pose* out) { store(load(a) * load(b), out); }
 void host_pose_inverse(const emvs_pose& a, emvs_pose* out) { store(load(a).inverse(), out); }
+
+// ---- rectification LUT (precomputeRectifiedPoints, mapper_emvs_stereo.cpp:244-299) -------------------
+// The reference fills the LUT with image_geometry::PinholeCameraModel::rectifyPoint (plumb_bob: a float
+// pixel through cv::undistortPoints(K, D, R, P), 5 fixed-point iterations, result stored as float; all-zero
+// D returns the raw pixel) or cv::fisheye::undistortPoints (equidistant model, Newton iterations on theta,
+// COUNT 10 + EPS 1e-8).  OpenCV is not part of the reference tree; both are restated from OpenCV 4.x
+// (calib3d/undistort.dispatch.cpp, fisheye.cpp) and pinned against this image's cv2 in
+// tests/test_rectify_lut.py.
+static void mat3_mul_d(const double* a, const double* b, double* o)
+{
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += a[3 * i + k] * b[3 * k + j];
+      o[3 * i + j] = s;
+    }
+}
+
+int host_rectify_lut(int model, const double K[9], const double* D, int n_d, const double R[9], const double P[12],
+                     uint32_t W, uint32_t H, float* out)
+{
+  if (model != EMVS_DISTORTION_NONE && model != EMVS_DISTORTION_PLUMB_BOB && model != EMVS_DISTORTION_FISHEYE) return 1;
+  double k[14] = {0};
+  for (int i = 0; i < n_d && i < 14; ++i) k[i] = D[i];
+  bool all_zero = true;
+  for (int i = 0; i < 14; ++i) all_zero = all_zero && k[i] == 0.0;
+  const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+  const double PP[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]};
+  double RR[9];
+  mat3_mul_d(PP, R, RR);
+  const double ifx = 1. / fx, ify = 1. / fy;
+  for (uint32_t py = 0; py < H; ++py)
+    for (uint32_t px = 0; px < W; ++px) {
+      float* o = out + 2 * ((size_t)py * W + px);
+      if (model == EMVS_DISTORTION_NONE || (model == EMVS_DISTORTION_PLUMB_BOB && all_zero)) {
+        o[0] = (float)px; o[1] = (float)py;   // image_geometry: distortion_state NONE -> the raw pixel
+        continue;
+      }
+      const double u = (double)(float)px, v = (double)(float)py;
+      if (model == EMVS_DISTORTION_PLUMB_BOB) {
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+          const double r2 = x * x + y * y;
+          const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+          if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+          const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+          const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+          x = (x0 - deltaX) * icdist;
+          y = (y0 - deltaY) * icdist;
+        }
+        const double xx = RR[0] * x + RR[1] * y + RR[2], yy = RR[3] * x + RR[4] * y + RR[5];
+        const double ww = 1. / (RR[6] * x + RR[7] * y + RR[8]);
+        o[0] = (float)(xx * ww); o[1] = (float)(yy * ww);
+      } else {
+        const double pwx = (u - cx) / fx, pwy = (v - cy) / fy;
+        double theta_d = std::sqrt(pwx * pwx + pwy * pwy);
+        const double half_pi = 3.1415926535897932384626433832795 / 2.;
+        theta_d = std::min(std::max(-half_pi, theta_d), half_pi);
+        bool converged = false;
+        double theta = theta_d, scale = 0.0;
+        const double eps = 1e-8;
+        if (std::fabs(theta_d) > eps) {
+          for (int j = 0; j < 10; ++j) {
+            const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+            const double k0 = k[0] * t2, k1 = k[1] * t4, k2 = k[2] * t6, k3 = k[3] * t8;
+            const double fix = (theta * (1 + k0 + k1 + k2 + k3) - theta_d) / (1 + 3 * k0 + 5 * k1 + 7 * k2 + 9 * k3);
+            theta = theta - fix;
+            if (std::fabs(fix) < eps) { converged = true; break; }
+          }
+          scale = std::tan(theta) / theta_d;
+        } else {
+          converged = true;
+        }
+        const bool flipped = (theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0);
+        if (converged && !flipped) {
+          const double ux = pwx * scale, uy = pwy * scale;
+          const double r0 = RR[0] * ux + RR[1] * uy + RR[2], r1 = RR[3] * ux + RR[4] * uy + RR[5];
+          const double r2 = RR[6] * ux + RR[7] * uy + RR[8];
+          o[0] = (float)(r0 / r2); o[1] = (float)(r1 / r2);
+        } else {
+          o[0] = -1000000.f; o[1] = -1000000.f;
+        }
+      }
+    }
+  return 0;
+}
 
 size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
                       const emvs_pose& T_rv_w_pod, const emvs_camera& cam, const float virt[4], float z0,

@@ -179,6 +179,14 @@ EMVS_API int emvs_host_free(void* p);
 EMVS_API int emvs_depth_vector(const emvs_shape* shape, float* out_depths /* dimZ */);
 /* Virtual camera of the DSI (MAP:219-239): out = {fx, fy, cx, cy}. */
 EMVS_API int emvs_virtual_camera(const emvs_camera* cam, const emvs_shape* shape, float out[4]);
+/* MapperEMVS::precomputeRectifiedPoints (MAP:244-299): the raw-pixel -> rectified-pixel LUT, out =
+ * width*height interleaved (x,y) floats indexed y*width + x.  K (3x3), R (3x3), P (3x4) row-major as in
+ * sensor_msgs/CameraInfo; D = k1,k2,p1,p2[,k3[,k4,k5,k6[,s1..s4[,tx,ty]]]] for plumb_bob (as
+ * image_geometry::rectifyPoint -> cv::undistortPoints; all-zero D returns the raw pixel) or k1..k4 for fisheye
+ * (cv::fisheye::undistortPoints).  Any other model is the reference's "Distortion model not set properly!". */
+enum { EMVS_DISTORTION_NONE = 0, EMVS_DISTORTION_PLUMB_BOB = 1, EMVS_DISTORTION_FISHEYE = 2 };
+EMVS_API int emvs_rectify_lut(int distortion_model, const double K[9], const double* D, int n_d, const double R[9],
+                     const double P[12], uint32_t width, uint32_t height, float* out_lut_xy);
 /* LinearTrajectory::getPoseAt (TRJ:92-127).  *found = 0 when t is outside the control poses. */
 EMVS_API int emvs_trajectory_pose_at(const emvs_stamped_pose* traj, size_t n_poses, uint32_t sec, uint32_t nsec,
                             emvs_pose* out, int* found);
