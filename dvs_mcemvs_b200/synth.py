@@ -45,8 +45,8 @@ def _split_time(t):
 
 
 # ------------------------------------------------------------------------------------------
-# rectification LUT for plumb_bob distortion (stand-in for image_geometry::rectifyPoint,
-# mapper_emvs_stereo.cpp:284 — the LUT is an INPUT of the engine)
+# forward plumb_bob distortion, used to place synthetic events on RAW (distorted) pixels; the inverse
+# (the rectification LUT) comes from the engine's own precomputeRectifiedPoints restatement
 # ------------------------------------------------------------------------------------------
 def distort(xn, yn, D):
     k1, k2, p1, p2 = D[:4]
@@ -56,20 +56,6 @@ def distort(xn, yn, D):
     xd = xn * rad + 2 * p1 * xn * yn + p2 * (r2 + 2 * xn * xn)
     yd = yn * rad + p1 * (r2 + 2 * yn * yn) + 2 * p2 * xn * yn
     return xd, yd
-
-
-def plumb_bob_lut(width, height, K, D, P):
-    """raw pixel -> rectified pixel, iterative inverse of the distortion model (R = identity)."""
-    xs, ys = np.meshgrid(np.arange(width, dtype=np.float64), np.arange(height, dtype=np.float64))
-    xd = (xs - K[2]) / K[0]
-    yd = (ys - K[3]) / K[1]
-    xn, yn = xd.copy(), yd.copy()
-    for _ in range(30):
-        ex, ey = distort(xn, yn, D)
-        xn -= ex - xd
-        yn -= ey - yd
-    lut = np.stack([xn * P[0] + P[2], yn * P[1] + P[3]], axis=-1)
-    return lut.astype(np.float32)
 
 
 # ------------------------------------------------------------------------------------------
@@ -89,15 +75,23 @@ def rig_esim():
     return Rig(cams, [0.0, 0.2])
 
 
+# cv::getOptimalNewCameraMatrix(K_left, D_left, (640, 480), alpha=0) evaluated once with OpenCV 4.13; the
+# reference computes it at start-up (calib.cpp:475-476) and reuses the LEFT camera's P for the right one (:482-488).
+_DSEC_P = (557.9686136352767, 558.0457356705808, 345.95312896446654, 217.50102178331326)
+
+
 def rig_dsec():
     Ks = [(553.4686750102932, 553.3994078799127, 346.65339162053317, 216.52092103243012),
           (552.1819422959984, 551.4454720096484, 336.87432177064744, 226.32630571403274)]
     Ds = [(-0.09356476362537607, 0.19445779814646236, 7.642434980998821e-05, 0.0019563864604273664),
           (-0.09493681546997375, 0.2021148065491477, 0.0005821287651820125, 0.0014552921745527136)]
+    fx, fy, cx, cy = _DSEC_P
+    P = [[fx, 0, cx, 0], [0, fy, cy, 0], [0, 0, 1, 0]]
     cams, raw = [], []
     for K, D in zip(Ks, Ds):
-        P = K  # projection matrix == K (stand-in for cv::getOptimalNewCameraMatrix(alpha=0), calib.cpp:476)
-        cams.append(CameraModel(640, 480, P[0], P[1], P[2], P[3], lut=plumb_bob_lut(640, 480, K, D, P)))
+        Km = [[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]]
+        # the LUT exactly as precomputeRectifiedPoints builds it (image_geometry::rectifyPoint -> cv::undistortPoints)
+        cams.append(CameraModel.from_camera_info(640, 480, Km, D, np.eye(3), P, "plumb_bob"))
         raw.append((K, D))
     return Rig(cams, [0.0, 0.599], raw)
 
