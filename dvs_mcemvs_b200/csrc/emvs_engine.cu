@@ -84,6 +84,7 @@ struct emvs_context {
   bool mark_consumed = false;          // build_on_device records ev_consumed after the event stage
   float2* d_xy0 = nullptr;   size_t xy0_cap = 0;
   void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
+  void* d_fc_part = nullptr; size_t fc_part_cap = 0;  // per-chunk (max, index) of the Z-split sweep
   double* d_partial = nullptr;                        // 1024 partial sums + 1 result
   // pinned host staging for packets produced by evaluate_dsi
   emvs_packet* h_packets = nullptr; size_t h_packets_cap = 0;
@@ -335,10 +336,33 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
   cudaStream_t st = ctx->stream;
   // (A float4-per-thread variant with the Z range split over warps was measured slower than this
   // one-pixel-per-thread sweep — 0.234 vs 0.209 ms for two 640x480x256 volumes, profiles/r1_fuse_collapse.md.)
-#define LAUNCH(N) \
-  k_fuse_collapse<METHOD, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth)
+  // EMVS_FC_ZSPLIT = c > 1: split the planes over c CTAs per pixel tile + a combine pass (tuning).
+  static const int zsplit_env = [] { const char* e = getenv("EMVS_FC_ZSPLIT"); return e ? atoi(e) : 1; }();
+  const uint32_t n_chunks = (uint32_t)std::max(1, std::min<int>(zsplit_env, (int)((dimZ + 7) / 8)));
+  float* part_best = nullptr;
+  uint32_t* part_k = nullptr;
+  uint32_t per_chunk = dimZ;
+  if (n_chunks > 1) {
+    const int rc = grow(&ctx->d_fc_part, &ctx->fc_part_cap, (size_t)n_chunks * n_pix * 8);
+    if (rc) return rc;
+    part_best = (float*)ctx->d_fc_part;
+    part_k = (uint32_t*)((char*)ctx->d_fc_part + (size_t)n_chunks * n_pix * 4);
+    per_chunk = (dimZ + n_chunks - 1) / n_chunks;
+  }
+  const uint32_t used_chunks = n_chunks > 1 ? (dimZ + per_chunk - 1) / per_chunk : 1;
+#define LAUNCH_M(M, N)                                                                                                     \
+  do {                                                                                                                     \
+    if (n_chunks > 1) {                                                                                                    \
+      k_fuse_collapse_zsplit<M, N><<<dim3(blocks, used_chunks), 128, 0, st>>>(A, n_pix, dimZ, per_chunk, fused, part_best, part_k); \
+      k_fc_combine<<<(n_pix + 255) / 256, 256, 0, st>>>(part_best, part_k, used_chunks, n_pix, d_depths, conf, idx, idx_bytes, depth); \
+      ctx->launches++;                                                                                                     \
+    } else {                                                                                                               \
+      k_fuse_collapse<M, N><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth);          \
+    }                                                                                                                      \
+  } while (0)
+#define LAUNCH(N) LAUNCH_M(METHOD, N)
   switch (A.n) {
-    case 1: k_fuse_collapse<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, st>>>(A, n_pix, dimZ, d_depths, fused, conf, idx, idx_bytes, depth); break;
+    case 1: LAUNCH_M(EMVS_FUSE_MAX, 1); break;
     case 2: LAUNCH(2); break;
     case 3: LAUNCH(3); break;
     case 4: LAUNCH(4); break;
@@ -349,6 +373,7 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
     default: set_error("fuse_collapse: need 1..8 grids"); return EMVS_ERR_INVALID;
   }
 #undef LAUNCH
+#undef LAUNCH_M
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return EMVS_OK;
@@ -489,6 +514,7 @@ static void context_release(emvs_context* ctx)
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_xy0);
   cudaFree(ctx->d_out);
+  cudaFree(ctx->d_fc_part);
   cudaFree(ctx->d_partial);
   if (ctx->h_packets) cudaFreeHost(ctx->h_packets);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
