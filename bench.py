@@ -172,6 +172,16 @@ def cpu_reference(args, n_full):
     t_argmax = time.perf_counter() - t0
     t_full = t_build * (n_full / n_s) + t_fuse + t_argmax
     n_cams = len(cams)
+    ref_code = None
+    try:   # the reference's OWN Grid3D code (compiled in place into oracle/_ref) for the fusion + argmax stage
+        from oracle import ref as R
+        if R.available():
+            f_ms, a_ms, conf_r, _ = R.time_fuse_collapse(vols[0], vols[1], method)
+            ref_code = {"fuse_ms": f_ms, "argmax_ms": a_ms, "depth_map_ms": f_ms + a_ms,
+                        "what": "cartesian3dgrid.h fusion ops (by-value argument, .at()) + Grid3D::collapseMaxZSlice compiled "
+                                "from the reference sources (oracle/_ref); the build stage has no compilable reference"}
+    except Exception as e:   # never let the extra baseline break the bench line
+        ref_code = {"unavailable": str(e)[:200]}
     return {
         "value": n_cams * n_full / t_full / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
         "sample": (f"{n_s} events/camera x {n_cams} cameras voted into the full 640x480x256 DSI by the oracle "
@@ -180,7 +190,7 @@ def cpu_reference(args, n_full):
                    + ("" if n_s == n_full else f"; build time scaled x{n_full / n_s:.1f} to {n_full} events/camera")),
         "build_mevents_per_s": n_cams * n_s / t_build / 1e6,
         "depth_map_ms": (t_fuse + t_argmax) * 1e3, "fuse_ms": t_fuse * 1e3, "argmax_ms": t_argmax * 1e3,
-        "sample_build_s": t_build, "host_cpus": os.cpu_count(),
+        "sample_build_s": t_build, "host_cpus": os.cpu_count(), "reference_code_depth_map": ref_code,
     }, t_full
 
 

@@ -41,6 +41,8 @@ def lib():
         L.ref_mean_square.restype = C.c_double
         L.ref_depth_vector.argtypes = [C.c_int, f32, f32, u64, vp]
         L.ref_huang_median.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.ref_time_fuse_collapse.argtypes = [u32, u32, u32, vp, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, vp]
+        L.ref_time_fuse_collapse.restype = C.c_int
         _lib = L
     return _lib
 
@@ -94,3 +96,17 @@ def huang_median(img, mask, patch_size):
     out = np.zeros_like(img)
     lib().ref_huang_median(_p(img), _p(mask), img.shape[0], img.shape[1], int(patch_size), _p(out))
     return out
+
+
+def time_fuse_collapse(a, b, method):
+    """Wall-clock ms of the reference's own fusion (process1.cpp:126-166) and collapseMaxZSlice on two volumes
+    -> (fuse_ms, argmax_ms, conf, idx)."""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    dimZ, dimY, dimX = a.shape
+    conf = np.zeros((dimY, dimX), np.float32)
+    idx = np.zeros((dimY, dimX), np.uint8)
+    f, m = C.c_double(0), C.c_double(0)
+    rc = lib().ref_time_fuse_collapse(dimX, dimY, dimZ, _p(a), _p(b), int(method), C.byref(f), C.byref(m), _p(conf), _p(idx))
+    if rc:
+        raise ValueError("Improper fusion method selected")
+    return f.value, m.value, conf, idx

@@ -6,6 +6,7 @@
 #include <mapper_emvs_stereo/depth_vector.hpp>
 #include <mapper_emvs_stereo/median_filtering.hpp>
 
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 
@@ -80,6 +81,41 @@ void ref_huang_median(const uint8_t* img, const uint8_t* mask, int rows, int col
   cv::Mat mi(rows, cols, CV_8U, (void*)img), mm(rows, cols, CV_8U, (void*)mask), mo;
   huangMedianFilter(mi, mo, mm, patch_size);
   std::memcpy(out, mo.data, (size_t)rows * cols);
+}
+
+// Times the reference's OWN fusion + argmax code on two volumes, in the order process_1 issues it
+// (process1.cpp:126-166: fused.resetGrid(); fused.addTwoGrids(dsi0); fused.<op>TwoGrids(dsi1)) followed by
+// collapseMaxZSlice (mapper_emvs_stereo.cpp:367-369).  The by-value argument copies and .at() bounds checks
+// are the reference's.  method: stereo_fusion id 1..6.  Loading the inputs is outside the timed scopes.
+int ref_time_fuse_collapse(uint32_t dimX, uint32_t dimY, uint32_t dimZ, const float* a, const float* b, int method,
+                           double* fuse_ms, double* argmax_ms, float* conf, uint8_t* idx)
+{
+  using clock = std::chrono::high_resolution_clock;
+  Grid3D g0(dimX, dimY, dimZ), g1(dimX, dimY, dimZ), fused(dimX, dimY, dimZ);
+  const size_t cells = (size_t)dimX * dimY * dimZ;
+  load(g0, a, cells);
+  load(g1, b, cells);
+  auto t0 = clock::now();
+  fused.resetGrid();
+  fused.addTwoGrids(g0);
+  switch (method) {
+    case 1: fused.minTwoGrids(g1); break;
+    case 2: fused.harmonicMeanTwoGrids(g1); break;
+    case 3: fused.geometricMeanTwoGrids(g1); break;
+    case 4: fused.arithmeticMeanTwoGrids(g1); break;
+    case 5: fused.rmsTwoGrids(g1); break;
+    case 6: fused.maxTwoGrids(g1); break;
+    default: return 1;
+  }
+  auto t1 = clock::now();
+  cv::Mat mv, mi;
+  fused.collapseMaxZSlice(&mv, &mi);
+  auto t2 = clock::now();
+  *fuse_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  *argmax_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+  if (conf) std::memcpy(conf, mv.data, (size_t)dimX * dimY * sizeof(float));
+  if (idx) std::memcpy(idx, mi.data, (size_t)dimX * dimY);
+  return 0;
 }
 
 // Grid3D::computeMeanSquare.  cartesian3dgrid.cpp:164-174
