@@ -322,14 +322,17 @@ def run_b200(args):
     n_launch = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # stage split (separate, untimed-for-value pass): build vs depth-map
+    # stage split (a separate pass, not part of `value`): build vs depth-map (vs multi-GPU exchange)
     barrier()
     t_build.start()
     for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
-        m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk))
+        m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None)
     t_build.stop()
     t_depth.start()
-    collapse_device()
+    if peer is not None:
+        peer.fuse_collapse(method, d_tab)    # reduce over NVLink + fuse + argmax in one sweep (+ the epoch waits)
+    else:
+        collapse_device()
     t_depth.stop()
     ctx.sync()
     build_ms, depth_ms = t_build.elapsed_ms(), t_depth.elapsed_ms()
@@ -423,6 +426,10 @@ def run_b200(args):
                        "l2": "inputs+DSIs (>700 MB/step) exceed the 126 MB L2; no explicit flush"},
             "build_mevents_per_s": n_cams * n_ev / (build_ms * 1e-3) / 1e6, "build_ms": build_ms,
             "depth_map_ms": depth_ms, "accepted_votes_per_step": votes,
+            "stage_note": ("build_ms = event stage + reset + votes + merges of both cameras; depth_map_ms = fuse + argmax + index->depth"
+                           + ("" if world == 1 else
+                              " INCLUDING the cross-GPU reduction over NVLink peer memory and the epoch waits" if peer is not None else
+                              "; the slab-wise ncclAllReduce runs inside build_ms, overlapped with voting")),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
