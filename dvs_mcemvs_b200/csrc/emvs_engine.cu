@@ -336,9 +336,9 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
   cudaStream_t st = ctx->stream;
   // (A float4-per-thread variant with the Z range split over warps was measured slower than this
   // one-pixel-per-thread sweep — 0.234 vs 0.209 ms for two 640x480x256 volumes, profiles/r1_fuse_collapse.md.)
-  // EMVS_FC_ZSPLIT = c > 1: split the planes over c CTAs per pixel tile + a combine pass (tuning).
-  static const int zsplit_env = [] { const char* e = getenv("EMVS_FC_ZSPLIT"); return e ? atoi(e) : 1; }();
-  const uint32_t n_chunks = (uint32_t)std::max(1, std::min<int>(zsplit_env, (int)((dimZ + 7) / 8)));
+  // The planes are split over 4 CTAs per pixel tile + a combine pass: 0.196 vs 0.209 ms (EMVS_FC_ZSPLIT overrides).
+  static const int zsplit_env = [] { const char* e = getenv("EMVS_FC_ZSPLIT"); return e ? atoi(e) : 4; }();
+  const uint32_t n_chunks = (uint32_t)std::max(1, std::min<int>(zsplit_env, (int)(dimZ / 16)));   // at least 16 planes per chunk
   float* part_best = nullptr;
   uint32_t* part_k = nullptr;
   uint32_t per_chunk = dimZ;
