@@ -80,7 +80,43 @@ int main()
           if (std::fabs(z[idx.at(y, x)] - Zstar) <= 2 * (5.0f - 1.0f) / 64 + 1e-4f) ++good;
         }
     std::printf("confident pixels: %zu, on the Z* = %.2f m plane (+-2 cells: events are rounded to integer pixels): %zu\n", total, Zstar, good);
-    const bool ok = total > 500 && good >= total * 90 / 100;
+    bool ok = total > 500 && good >= total * 90 / 100;
+
+    // --- getDepthMapFromDSI with the reference's options (adaptive threshold + masked median + border) ---
+    EMVS::OptionsDepthMap opts;          // defaults of main.cpp: kernel 5, C 5, median 5, max_confidence 0
+    emvs_host::Image<float> depth_sd, conf_sd;
+    emvs_host::Image<uint8_t> mask, idx_f;
+    mapper_fused.getDepthMapFromDSI(depth_sd, conf_sd, mask, opts, &idx_f);
+    size_t n_mask = 0, n_mask_on_plane = 0;
+    for (int y = 0; y < (int)H; ++y)
+      for (int x = 0; x < (int)W; ++x)
+        if (mask.at(y, x)) {
+          ++n_mask;
+          if (std::fabs(depth_sd.at(y, x) - Zstar) <= 3 * (5.0f - 1.0f) / 64 + 1e-4f) ++n_mask_on_plane;
+        }
+    std::printf("semi-dense mask: %zu pixels, %zu within 3 cells of Z*\n", n_mask, n_mask_on_plane);
+    ok = ok && n_mask > 500 && n_mask_on_plane >= n_mask * 80 / 100 && mask.at(0, 0) == 0 && mask.at(2, 2) == 0;
+
+    // --- Grid3D voxel ops and the .npy writer through the mirror ---
+    Grid3D a(4, 3, 2), b(4, 3, 2);
+    std::vector<float> va(24), vb(24);
+    for (int i = 0; i < 24; ++i) { va[i] = (float)i; vb[i] = (float)(24 - i); }
+    a.upload(va.data());
+    b.upload(vb.data());
+    a.harmonicMeanTwoGrids(b);                       // 2ab / (a + b + 0.1)
+    const float want = 2.f * (5.f * 19.f) / (5.f + 19.f + 0.1f);
+    ok = ok && a.getGridValueAt(1, 1, 0) == want;    // p = 1 + 4*(1 + 3*0) = 5
+    a.maxTwoGrids(b);
+    ok = ok && a.getGridValueAt(0) == 24.f && std::fabs(a.computeMeanSquare() - b.computeMeanSquare()) < 400.0;
+    const char* npy = "/tmp/emvs_example_dsi.npy";
+    ok = ok && mapper0.dsi_.writeGridNpy(npy) == 0;
+    if (FILE* f = std::fopen(npy, "rb")) {
+      std::fseek(f, 0, SEEK_END);
+      const long sz = std::ftell(f);
+      std::fclose(f);
+      std::printf("wrote %s: %ld bytes\n", npy, sz);
+      ok = ok && sz == 128 + (long)W * H * 64 * 4;
+    } else ok = false;
     std::printf(ok ? "example_process1 ok\n" : "example_process1 FAILED\n");
     return ok ? 0 : 1;
   } catch (const std::exception& e) {

@@ -18,3 +18,16 @@ def test_two_rank_sharded_build_matches_unsharded():
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "mgpu_check ok" in r.stdout
+
+
+def test_host_cpp_mirror_example():
+    """The C++ caller written against the reference's class API (Grid3D, EMVS::MapperEMVS, LinearTrajectory, process_1,
+    getDepthMapFromDSI with options, writeGridNpy) passes its known-answer checks."""
+    import numpy as np
+    exe = os.path.join(ROOT, "dvs_mcemvs_b200", "host", "example_process1")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(exe)], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "example_process1 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    vol = np.load("/tmp/emvs_example_dsi.npy")                     # what the reference's viewers read
+    assert vol.shape == (64, 180, 240) and vol.dtype == np.float32 and vol.sum() > 1e4
