@@ -411,6 +411,10 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
                 "avg_launch_ms": vote_ms_per_step / launches_per_step, "launches_per_step": launches_per_step,
                 "kernel_share_of_step": vote_ms_per_step / ms_step,
+                "physical_bound": {"what": "RED sectors retired by the L1/L2 path (one 16-byte red.global.add.v4.f32 per vote)",
+                                   "achieved_gsectors_per_s": votes / (vote_ms_per_step * 1e-3) / 1e9,
+                                   "microbench_ceiling_gsectors_per_s": 185.0,
+                                   "source": "profiles/r1_red_microbench.csv (random 16-byte REDs, L2-resident footprint)"},
                 "note": "uncached-scatter model: votes resolve as red.global.add.v4.f32 in an L2-resident slab, so "
                         "a fraction above what DRAM counters show is cache-served, see DESIGN.md §4"}
         out = {
