@@ -1486,22 +1486,34 @@ static int launch_peer(emvs_exchange* ex, const float* d_depths, uint32_t p_lo, 
 {
   emvs_context* ctx = ex->ctx;
   const uint32_t n_pix = ex->dimX * ex->dimY;
-  const unsigned blocks = (p_hi - p_lo + 127) / 128;
+  const uint32_t band = p_hi - p_lo;
+  const unsigned blocks = (band + 127) / 128;
   const int idx_bytes = ex->dimZ <= 256 ? 1 : 2;
   unsigned int* err = ex->flags + 2 * kMaxPeerRanks;
-#define LAUNCH(N)                                                                                                       \
-  k_fuse_collapse_peer<METHOD, N><<<blocks, 128, 0, ctx->stream>>>(ex->args, ex->flags, ex->epoch, timeout, err, p_lo, p_hi, \
-                                                                   n_pix, ex->dimZ, d_depths, idx_bytes)
+  // plane chunks: enough CTAs to cover the NVLink latency (EMVS_PEER_ZSPLIT overrides), >= 8 planes per chunk
+  static const int zs_env = [] { const char* e = getenv("EMVS_PEER_ZSPLIT"); return e ? atoi(e) : 8; }();
+  const uint32_t n_chunks = (uint32_t)std::max(1, std::min<int>(zs_env, (int)(ex->dimZ / 8)));
+  const uint32_t per_chunk = (ex->dimZ + n_chunks - 1) / n_chunks;
+  const uint32_t used = (ex->dimZ + per_chunk - 1) / per_chunk;
+  int rc = grow(&ctx->d_fc_part, &ctx->fc_part_cap, (size_t)used * band * 8);
+  if (rc) return rc;
+  float* part_best = (float*)ctx->d_fc_part;
+  uint32_t* part_k = (uint32_t*)((char*)ctx->d_fc_part + (size_t)used * band * 4);
+  const dim3 grid(blocks, used);
+#define LAUNCH(M, N)                                                                                                       \
+  k_fuse_collapse_peer<M, N><<<grid, 128, 0, ctx->stream>>>(ex->args, ex->flags, ex->epoch, timeout, err, p_lo, p_hi, n_pix, \
+                                                            ex->dimZ, per_chunk, part_best, part_k)
   switch (ex->n_cams) {
-    case 1: k_fuse_collapse_peer<EMVS_FUSE_MAX, 1><<<blocks, 128, 0, ctx->stream>>>(ex->args, ex->flags, ex->epoch, timeout, err,
-                                                                                  p_lo, p_hi, n_pix, ex->dimZ, d_depths, idx_bytes); break;
-    case 2: LAUNCH(2); break;
-    case 3: LAUNCH(3); break;
-    case 4: LAUNCH(4); break;
+    case 1: LAUNCH(EMVS_FUSE_MAX, 1); break;
+    case 2: LAUNCH(METHOD, 2); break;
+    case 3: LAUNCH(METHOD, 3); break;
+    case 4: LAUNCH(METHOD, 4); break;
     default: break;
   }
 #undef LAUNCH
-  ctx->launches++;
+  k_peer_combine_store<<<(band + 255) / 256, 256, 0, ctx->stream>>>(ex->args, part_best, part_k, used, p_lo, p_hi, d_depths,
+                                                                      idx_bytes, err);
+  ctx->launches += 2;
   return EMVS_OK;
 }
 
