@@ -287,8 +287,11 @@ def run_b200(args):
         peer = api.PeerExchange(ctx, grids, world, rank, allgather)
 
     def step_device():
+        if peer is not None:
+            peer.begin()      # slab-wise band reduce over NVLink, overlapped with voting
         for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
-            m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None)
+            m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None,
+                           peer_reduce=peer is not None)
         if peer is not None:
             peer.fuse_collapse(method, d_tab)
         else:
@@ -324,9 +327,12 @@ def run_b200(args):
 
     # stage split (a separate pass, not part of `value`): build vs depth-map (vs multi-GPU exchange)
     barrier()
+    if peer is not None:
+        peer.begin()
     t_build.start()
     for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
-        m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None)
+        m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None,
+                       peer_reduce=peer is not None)
     t_build.stop()
     t_depth.start()
     if peer is not None:
@@ -349,11 +355,10 @@ def run_b200(args):
             h_events.append(buf)
 
         def step_host():
+            if peer is not None:
+                peer.begin()
             for m, ev, tr in zip(mappers, h_events, ltrajs):
-                if world > 1 and peer is None:   # sharded: host packet stage, then this rank's build with slab-wise allreduce
-                    m.build(ev, m.packetize(ev, tr, T_rv_w), allreduce=True)
-                else:
-                    assert m.evaluateDSI(ev, tr, T_rv_w)
+                assert m.evaluateDSI(ev, tr, T_rv_w, allreduce=world > 1 and peer is None, peer_reduce=peer is not None)
             if peer is not None:
                 peer.fuse_collapse(method, d_tab)
                 return peer.download()
@@ -424,7 +429,7 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "description": desc, "events_per_camera_per_gpu": n_ev, "cameras": n_cams,
                        "dsi": [dimX, dimY, dimZ], "fusion": "harmonic", "event_distribution": args.kind,
                        "sharding": ("none" if world == 1 else
-                                    "event sub-interval per GPU; fused reduce+fuse+argmax sweep over NVLink peer memory (row band per GPU)"
+                                    "event sub-interval per GPU; slab-wise reduce of each GPU's row band over NVLink peer memory under the votes, then fuse+argmax of the band and peer stores of the maps"
                                     if peer is not None else
                                     "event sub-interval per GPU; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting"),
                        "l2": "inputs+DSIs (>700 MB/step) exceed the 126 MB L2; no explicit flush"},
@@ -432,7 +437,7 @@ def run_b200(args):
             "depth_map_ms": depth_ms, "accepted_votes_per_step": votes,
             "stage_note": ("build_ms = event stage + reset + votes + merges of both cameras; depth_map_ms = fuse + argmax + index->depth"
                            + ("" if world == 1 else
-                              " INCLUDING the cross-GPU reduction over NVLink peer memory and the epoch waits" if peer is not None else
+                              " of this GPU's row band + distribution of the maps; the slab-wise peer reduce runs inside build_ms" if peer is not None else
                               "; the slab-wise ncclAllReduce runs inside build_ms, overlapped with voting")),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof,
         }

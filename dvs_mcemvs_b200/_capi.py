@@ -20,7 +20,7 @@ PACKET_SIZE = 1024
 FUSE_MIN, FUSE_HM, FUSE_GM, FUSE_AM, FUSE_RMS, FUSE_MAX = 1, 2, 3, 4, 5, 6
 (OP_ADD, OP_MIN, OP_HM, OP_GM, OP_AM, OP_RMS, OP_MAX, OP_HM_N, OP_ADD_INV, OP_HM_FROM_SUMINV,
  OP_AM_FROM_SUM) = range(11)
-BUILD_RESET, BUILD_ACCUMULATE, BUILD_ALLREDUCE = 0, 1, 2
+BUILD_RESET, BUILD_ACCUMULATE, BUILD_ALLREDUCE, BUILD_PEER_REDUCE = 0, 1, 2, 4
 DISTORTION_NONE, DISTORTION_PLUMB_BOB, DISTORTION_FISHEYE = 0, 1, 2
 
 # numpy views of the POD structs (layouts asserted against the C side in tests/test_abi.py)
@@ -108,6 +108,7 @@ _PROTOTYPES = {
     "emvs_mapper_build": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.c_int]),
     "emvs_mapper_build_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.c_int]),
     "emvs_mapper_evaluate_dsi": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "emvs_mapper_evaluate_dsi_flags": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, C.c_int]),
     "emvs_mapper_counts": (C.c_int, [_vp, _vp]),
     "emvs_comm_unique_id": (C.c_int, [_vp]),
     "emvs_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -120,6 +121,7 @@ _PROTOTYPES = {
     "emvs_exchange_blob_bytes": (C.c_int, [_vp, C.POINTER(_sz)]),
     "emvs_exchange_export": (C.c_int, [_vp, _vp]),
     "emvs_exchange_import": (C.c_int, [_vp, _vp]),
+    "emvs_exchange_begin": (C.c_int, [_vp]),
     "emvs_exchange_fuse_collapse": (C.c_int, [_vp, C.c_int, _vp]),
     "emvs_exchange_maps": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "emvs_exchange_download": (C.c_int, [_vp, _vp, _vp, _vp]),

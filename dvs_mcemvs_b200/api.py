@@ -400,6 +400,11 @@ class PeerExchange:
 
     __del__ = close
 
+    def begin(self):
+        """Start an overlapped round: builds issued with peer_reduce=True until fuse_collapse() reduce every
+        Z-slab of this rank's row band over NVLink while the next slab is voted."""
+        check(_lib().emvs_exchange_begin(self._h))
+
     def fuse_collapse(self, method, d_depths=None):
         """Collective and asynchronous: call on every rank after its builds were issued."""
         check(_lib().emvs_exchange_fuse_collapse(self._h, int(method), C.c_void_p(d_depths) if d_depths else None))
@@ -459,33 +464,36 @@ class MapperEMVS:
         check(rc)
         return out[:n_pk.value]
 
-    def evaluateDSI(self, events, trajectory, T_rv_w):
-        """bool evaluateDSI(events, trajectory, T_rv_w) — mapper_emvs_stereo.cpp:67-148."""
+    def evaluateDSI(self, events, trajectory, T_rv_w, allreduce=False, peer_reduce=False):
+        """bool evaluateDSI(events, trajectory, T_rv_w) — mapper_emvs_stereo.cpp:67-148.
+        allreduce / peer_reduce: the events are this rank's shard of a multi-GPU build."""
         events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
-        rc = _lib().emvs_mapper_evaluate_dsi(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
-                                             trajectory.poses.shape[0],
-                                             ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE)))
+        rc = _lib().emvs_mapper_evaluate_dsi_flags(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
+                                                   trajectory.poses.shape[0],
+                                                   ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE)),
+                                                   self._flags(False, allreduce, peer_reduce))
         if rc == capi.EMVS_ERR_TOO_FEW:
             return False
         check(rc)
         return True
 
     @staticmethod
-    def _flags(accumulate, allreduce):
-        return (capi.BUILD_ACCUMULATE if accumulate else capi.BUILD_RESET) | (capi.BUILD_ALLREDUCE if allreduce else 0)
+    def _flags(accumulate, allreduce, peer_reduce=False):
+        return ((capi.BUILD_ACCUMULATE if accumulate else capi.BUILD_RESET) | (capi.BUILD_ALLREDUCE if allreduce else 0)
+                | (capi.BUILD_PEER_REDUCE if peer_reduce else 0))
 
-    def build(self, events, packets, accumulate=False, allreduce=False):
+    def build(self, events, packets, accumulate=False, allreduce=False, peer_reduce=False):
         """Event stage + reset + fillVoxelGrid (mapper_emvs_stereo.cpp:129-205) for given packets.
         allreduce=True: this is one rank's shard; Z-slabs are summed over the ranks while voting goes on."""
         events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
         packets = np.ascontiguousarray(packets, dtype=PACKET_DTYPE)
         check(_lib().emvs_mapper_build(self._h, ptr(events), events.shape[0], ptr(packets), packets.shape[0],
-                                       self._flags(accumulate, allreduce)))
+                                       self._flags(accumulate, allreduce, peer_reduce)))
 
-    def build_device(self, d_events, n_events, d_packets, n_packets, accumulate=False, allreduce=False):
+    def build_device(self, d_events, n_events, d_packets, n_packets, accumulate=False, allreduce=False, peer_reduce=False):
         """Same with device pointers (ints); asynchronous on the context's stream."""
         check(_lib().emvs_mapper_build_device(self._h, C.c_void_p(d_events), int(n_events), C.c_void_p(d_packets),
-                                              int(n_packets), self._flags(accumulate, allreduce)))
+                                              int(n_packets), self._flags(accumulate, allreduce, peer_reduce)))
 
     def depths_device_ptr(self):
         p = C.c_void_p()

@@ -91,7 +91,8 @@ struct emvs_context {
   // NCCL
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
-  cudaStream_t comm_stream = nullptr;      // slab allreduces run here, overlapped with the next slab's votes
+  cudaStream_t comm_stream = nullptr;      // slab allreduces / peer reduces run here, overlapped with the next slab's votes
+  struct emvs_exchange* active_exchange = nullptr;   // set by emvs_exchange_begin for EMVS_BUILD_PEER_REDUCE builds
   std::vector<cudaEvent_t> slab_events;    // slab s merged -> its allreduce may start
   cudaEvent_t ev_comm_done = nullptr;
   // optional per-launch timing of the vote kernel (bench roofline): event pairs on `stream`
@@ -118,6 +119,28 @@ struct emvs_mapper {
   bool lut_set = false;
   emvs_grid* grid = nullptr;
   unsigned long long* d_counts = nullptr;
+};
+
+constexpr uint32_t kMaxSlabs = 256;            // per camera, for the slab-wise peer reduce
+constexpr uint32_t kFlagWordsPhase = 32;        // [2][kMaxPeerRanks] phase epochs, word 16 = error, rest padding
+struct emvs_exchange {
+  emvs_context* ctx = nullptr;
+  int n_cams = 0, n_ranks = 1, rank = 0;
+  uint32_t dimX = 0, dimY = 0, dimZ = 0;
+  uint32_t row_lo = 0, row_hi = 0;               // the row band this rank owns
+  const float* local_dsi[kMaxPeerCams] = {};
+  char* maps = nullptr;            // conf | depth | idx of this rank (one allocation, IPC-exported)
+  size_t off_depth = 0, off_idx = 0, maps_bytes = 0;
+  // IPC-exported flag words: [0..15] phase epochs [2][kMaxPeerRanks], [16] error,
+  // [kFlagWordsPhase + ((cam * kMaxSlabs + slab) * kMaxPeerRanks + rank)] slab epochs
+  unsigned int* flags = nullptr;
+  float* band_buf = nullptr;       // [n_cams][dimZ][band pixels]: this rank's band summed over the ranks
+  PeerArgs args{};
+  FlagPtrs flag_ptrs{};
+  std::vector<void*> opened;       // cudaIpcOpenMemHandle mappings to close
+  unsigned int epoch = 0;
+  bool imported = false;
+  bool band_round = false;         // emvs_exchange_begin was called: builds reduce their slabs into band_buf
 };
 
 namespace {
@@ -196,7 +219,34 @@ int ncclAllReduceU64_checked(const NcclApi* api, emvs_context* ctx, unsigned lon
   return r;
 }
 
-// Device part of evaluateDSI: event stage, (reset), slab loop of {vote, merge, re-zero[, allreduce]}.
+// Slab-wise reduce-scatter over NVLink peer memory (EMVS_BUILD_PEER_REDUCE).  `after` is the stream on which
+// planes [k0, k0+nk) of camera `cam` become final on this rank (the merge stream): the "slab built" epoch is
+// published to every rank from there, and the band reduce is ordered behind it on the communication stream.
+int peer_reduce_slab(emvs_context* ctx, emvs_exchange* ex, int cam, uint32_t slab_idx, uint32_t k0, uint32_t nk,
+                     cudaStream_t after)
+{
+  REQUIRE(slab_idx < kMaxSlabs, EMVS_ERR_INVALID, "peer_reduce: slab index out of range");
+  const uint32_t word = kFlagWordsPhase + ((uint32_t)cam * kMaxSlabs + slab_idx) * kMaxPeerRanks;
+  k_flag_signal_word<<<1, 32, 0, after>>>(ex->flag_ptrs, ex->n_ranks, word + (uint32_t)ex->rank, ex->epoch);
+  while (ctx->slab_events.size() <= slab_idx) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->slab_events.push_back(e);
+  }
+  CUDA_TRY(cudaEventRecord(ctx->slab_events[slab_idx], after));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->slab_events[slab_idx], 0));
+  const uint32_t p_lo = ex->row_lo * ex->dimX, p_hi = ex->row_hi * ex->dimX, band = p_hi - p_lo;
+  if (band) {
+    const dim3 grid((band + 255) / 256, nk);
+    float* out = ex->band_buf + ((size_t)cam * ex->dimZ + k0) * band;
+    k_peer_reduce_band<<<grid, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch, 40000000000LL,
+                                                           ex->flags + 16, p_lo, p_hi, ex->dimX * ex->dimY, k0, nk, out);
+  }
+  ctx->launches += 2;
+  return EMVS_OK;
+}
+
+// Device part of evaluateDSI: event stage, (reset), slab loop of {vote, merge, re-zero[, allreduce | peer reduce]}.
 int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, const emvs_packet* d_pk,
                     size_t n_packets, int flags)
 {
@@ -205,6 +255,16 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   const bool accumulate = (flags & EMVS_BUILD_ACCUMULATE) != 0;
   const bool reduce = (flags & EMVS_BUILD_ALLREDUCE) != 0;
   cudaStream_t st = ctx->stream;
+  const bool peer = (flags & EMVS_BUILD_PEER_REDUCE) != 0;
+  emvs_exchange* ex = peer ? ctx->active_exchange : nullptr;
+  int peer_cam = -1;
+  if (peer) {
+    REQUIRE(!accumulate && !reduce, EMVS_ERR_INVALID, "build: EMVS_BUILD_PEER_REDUCE excludes ACCUMULATE and ALLREDUCE");
+    REQUIRE(ex && ex->band_round, EMVS_ERR_STATE, "build: EMVS_BUILD_PEER_REDUCE needs emvs_exchange_begin");
+    for (int c = 0; c < ex->n_cams; ++c)
+      if (ex->local_dsi[c] == g->d) peer_cam = c;
+    REQUIRE(peer_cam >= 0, EMVS_ERR_INVALID, "build: this mapper's DSI is not part of the active exchange");
+  }
   const NcclApi* nccl = nullptr;
   if (reduce) {
     REQUIRE(!accumulate, EMVS_ERR_INVALID, "build: EMVS_BUILD_ALLREDUCE cannot be combined with EMVS_BUILD_ACCUMULATE");
@@ -220,6 +280,10 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
     if (reduce) {  // this rank has no packets but must still take part in the collective
       if (ncclAllReduce_checked(nccl, ctx, g->d, g->n_cells, st)) return EMVS_ERR_NCCL;
       if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, g->dimZ, st)) return EMVS_ERR_NCCL;
+    }
+    if (peer) {    // an all-zero partial DSI: one "slab" covering every plane
+      const int rc = peer_reduce_slab(ctx, ex, peer_cam, 0, 0, g->dimZ, st);
+      if (rc) return rc;   // (emvs_exchange_fuse_collapse waits for the communication stream)
     }
     return EMVS_OK;
   }
@@ -297,6 +361,12 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       CUDA_TRY(cudaEventRecord(ctx->ev_merge[b], ms));
       ctx->merge_pending[b] = true;
     }
+    if (peer) {
+      // planes [k0, k0+nk) are final on this rank: tell every peer, then sum this rank's row band of those
+      // planes over all ranks into the band buffer on the communication stream, under the next slab's votes
+      const int rc = peer_reduce_slab(ctx, ex, peer_cam, (uint32_t)(k0 / slab), k0, nk, ms);
+      if (rc) return rc;
+    }
     if (reduce) {
       // planes [k0, k0+nk) are final on this rank: sum them over the ranks on the communication
       // stream while the next slab is being voted
@@ -318,6 +388,8 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_merge[b], 0));
       ctx->merge_pending[b] = false;
     }
+  // (peer mode: the band reduces keep running on the communication stream under the next camera's votes;
+  //  emvs_exchange_fuse_collapse waits for them)
   if (reduce) {
     // the vote counters are final once the last vote kernel ran (recorded by the last slab event)
     if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, dimZ, ctx->comm_stream)) return EMVS_ERR_NCCL;
@@ -1203,6 +1275,12 @@ int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_even
 int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
                              const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w)
 {
+  return emvs_mapper_evaluate_dsi_flags(m, events, n_events, traj, n_poses, T_rv_w, EMVS_BUILD_RESET);
+}
+
+int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                                   const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w, int flags)
+{
   REQUIRE(m && events && traj && T_rv_w, EMVS_ERR_INVALID, "evaluate_dsi: NULL argument");
   REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
   if (n_events < EMVS_PACKET_SIZE) {
@@ -1226,7 +1304,7 @@ int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_
   if (rc) return rc;
   const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
                                      ctx->h_packets, max_pk);
-  rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, EMVS_BUILD_RESET, true);
+  rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, flags, true);
   if (rc) return rc;
   if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // nothing waited for the event upload
   return EMVS_OK;
@@ -1342,21 +1420,6 @@ int emvs_mapper_counts_allreduce(emvs_mapper* m)
 }
 
 // ---- fused multi-GPU sweep over peer memory ------------------------------------------------------
-struct emvs_exchange {
-  emvs_context* ctx = nullptr;
-  int n_cams = 0, n_ranks = 1, rank = 0;
-  uint32_t dimX = 0, dimY = 0, dimZ = 0;
-  const float* local_dsi[kMaxPeerCams] = {};
-  char* maps = nullptr;            // conf | depth | idx of this rank (one allocation, IPC-exported)
-  size_t off_depth = 0, off_idx = 0, maps_bytes = 0;
-  unsigned int* flags = nullptr;   // [2][kMaxPeerRanks] epochs + 1 error word (IPC-exported)
-  PeerArgs args{};
-  FlagPtrs flag_ptrs{};
-  std::vector<void*> opened;       // cudaIpcOpenMemHandle mappings to close
-  unsigned int epoch = 0;
-  bool imported = false;
-};
-
 static const size_t kIpcBytes = sizeof(cudaIpcMemHandle_t);
 
 int emvs_exchange_create(emvs_context* ctx, emvs_grid* const* grids, int n_cams, int n_ranks, int rank, emvs_exchange** out)
@@ -1381,14 +1444,25 @@ int emvs_exchange_create(emvs_context* ctx, emvs_grid* const* grids, int n_cams,
   ex->off_depth = n_pix * 4;
   ex->off_idx = n_pix * 8;
   ex->maps_bytes = n_pix * 10;
+  {  // rows owned by this rank (balanced to within one row)
+    const uint32_t base = ex->dimY / n_ranks, extra = ex->dimY % n_ranks;
+    ex->row_lo = rank * base + std::min<uint32_t>(rank, extra);
+    ex->row_hi = ex->row_lo + base + ((uint32_t)rank < extra ? 1u : 0u);
+  }
+  const size_t flag_words = kFlagWordsPhase + (size_t)kMaxPeerCams * kMaxSlabs * kMaxPeerRanks;
+  const size_t band_bytes = std::max<size_t>(16, (size_t)n_cams * ex->dimZ * (ex->row_hi - ex->row_lo) * ex->dimX * sizeof(float));
   cudaError_t e = cudaMalloc((void**)&ex->maps, ex->maps_bytes);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&ex->flags, sizeof(unsigned int) * (2 * kMaxPeerRanks + 1));
-  if (e == cudaSuccess) e = cudaMemset(ex->flags, 0, sizeof(unsigned int) * (2 * kMaxPeerRanks + 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ex->flags, sizeof(unsigned int) * flag_words);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ex->band_buf, band_bytes);
+  if (e == cudaSuccess) e = cudaMemset(ex->flags, 0, sizeof(unsigned int) * flag_words);
   if (e == cudaSuccess) e = cudaMemset(ex->maps, 0, ex->maps_bytes);
+  if (e == cudaSuccess && !ctx->comm_stream) e = cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess && !ctx->ev_comm_done) e = cudaEventCreateWithFlags(&ctx->ev_comm_done, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     set_error("exchange_create: %s", cudaGetErrorString(e));
     cudaFree(ex->maps);
     cudaFree(ex->flags);
+    cudaFree(ex->band_buf);
     delete ex;
     return EMVS_ERR_CUDA;
   }
@@ -1402,9 +1476,12 @@ int emvs_exchange_destroy(emvs_exchange* ex)
   if (!ex) return EMVS_OK;
   DeviceGuard guard(ex->ctx->device);
   cudaStreamSynchronize(ex->ctx->stream);
+  if (ex->ctx->comm_stream) cudaStreamSynchronize(ex->ctx->comm_stream);
+  if (ex->ctx->active_exchange == ex) ex->ctx->active_exchange = nullptr;
   for (void* p : ex->opened) cudaIpcCloseMemHandle(p);
   cudaFree(ex->maps);
   cudaFree(ex->flags);
+  cudaFree(ex->band_buf);
   context_release(ex->ctx);
   delete ex;
   return EMVS_OK;
@@ -1517,7 +1594,53 @@ static int launch_peer(emvs_exchange* ex, const float* d_depths, uint32_t p_lo, 
   return EMVS_OK;
 }
 
+// Band round (emvs_exchange_begin + EMVS_BUILD_PEER_REDUCE builds): the band is already summed over the ranks
+// in band_buf [cam][Z][band]; a purely LOCAL fuse + argmax sweep, then the band goes to every rank's maps.
+template <int METHOD>
+static int launch_band_sweep(emvs_exchange* ex, const float* d_depths)
+{
+  emvs_context* ctx = ex->ctx;
+  const uint32_t p_lo = ex->row_lo * ex->dimX, p_hi = ex->row_hi * ex->dimX, band = p_hi - p_lo;
+  const int idx_bytes = ex->dimZ <= 256 ? 1 : 2;
+  const uint32_t n_chunks = std::max<uint32_t>(1, std::min<uint32_t>(8, ex->dimZ / 8));
+  const uint32_t per_chunk = (ex->dimZ + n_chunks - 1) / n_chunks;
+  const uint32_t used = (ex->dimZ + per_chunk - 1) / per_chunk;
+  int rc = grow(&ctx->d_fc_part, &ctx->fc_part_cap, (size_t)used * band * 8);
+  if (rc) return rc;
+  float* part_best = (float*)ctx->d_fc_part;
+  uint32_t* part_k = (uint32_t*)((char*)ctx->d_fc_part + (size_t)used * band * 4);
+  FuseArgs A{};
+  A.n = ex->n_cams;
+  A.method = METHOD;
+  for (int c = 0; c < ex->n_cams; ++c) A.g[c] = ex->band_buf + (size_t)c * ex->dimZ * band;
+  const dim3 grid((band + 127) / 128, used);
+#define LAUNCH(M, N) k_fuse_collapse_zsplit<M, N><<<grid, 128, 0, ctx->stream>>>(A, band, ex->dimZ, per_chunk, nullptr, part_best, part_k)
+  switch (ex->n_cams) {
+    case 1: LAUNCH(EMVS_FUSE_MAX, 1); break;
+    case 2: LAUNCH(METHOD, 2); break;
+    case 3: LAUNCH(METHOD, 3); break;
+    case 4: LAUNCH(METHOD, 4); break;
+    default: break;
+  }
+#undef LAUNCH
+  k_peer_combine_store<<<(band + 255) / 256, 256, 0, ctx->stream>>>(ex->args, part_best, part_k, used, p_lo, p_hi, d_depths,
+                                                                      idx_bytes, ex->flags + 16);
+  ctx->launches += 2;
+  return EMVS_OK;
+}
+
 extern "C" {
+
+int emvs_exchange_begin(emvs_exchange* ex)
+{
+  REQUIRE(ex, EMVS_ERR_INVALID, "exchange is NULL");
+  REQUIRE(ex->imported, EMVS_ERR_STATE, "exchange_begin: peers not imported (emvs_exchange_import)");
+  REQUIRE(!ex->band_round, EMVS_ERR_STATE, "exchange_begin: the previous round was not finished with emvs_exchange_fuse_collapse");
+  ex->epoch++;
+  ex->band_round = true;
+  ex->ctx->active_exchange = ex;
+  return EMVS_OK;
+}
 
 int emvs_exchange_fuse_collapse(emvs_exchange* ex, int method, const float* d_depths)
 {
@@ -1527,14 +1650,31 @@ int emvs_exchange_fuse_collapse(emvs_exchange* ex, int method, const float* d_de
   emvs_context* ctx = ex->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t st = ctx->stream;
-  ex->epoch++;
   ex->args.method = method;
   // ~20 s at 2 GHz: a peer that never arrives raises the error word instead of hanging the GPU
   const long long timeout = 40000000000LL;
-  // rows owned by this rank (balanced to within one row)
-  const uint32_t base = ex->dimY / ex->n_ranks, extra = ex->dimY % ex->n_ranks;
-  const uint32_t row_lo = ex->rank * base + std::min<uint32_t>(ex->rank, extra);
-  const uint32_t row_hi = row_lo + base + ((uint32_t)ex->rank < extra ? 1u : 0u);
+  const uint32_t row_lo = ex->row_lo, row_hi = ex->row_hi;
+  if (ex->band_round) {
+    // the builds of this round already reduced every slab of this rank's band into band_buf (stream-ordered
+    // before this point): local sweep, then store the band into every rank's maps
+    ex->band_round = false;
+    ctx->active_exchange = nullptr;
+    CUDA_TRY(cudaEventRecord(ctx->ev_comm_done, ctx->comm_stream));   // every slab reduce of this round
+    CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_comm_done, 0));
+    if (row_hi > row_lo) {
+      int rc = EMVS_OK;
+      switch (method) {
+        case EMVS_FUSE_MIN: rc = launch_band_sweep<EMVS_FUSE_MIN>(ex, d_depths); break;
+        case EMVS_FUSE_HM: rc = launch_band_sweep<EMVS_FUSE_HM>(ex, d_depths); break;
+        case EMVS_FUSE_GM: rc = launch_band_sweep<EMVS_FUSE_GM>(ex, d_depths); break;
+        case EMVS_FUSE_AM: rc = launch_band_sweep<EMVS_FUSE_AM>(ex, d_depths); break;
+        case EMVS_FUSE_RMS: rc = launch_band_sweep<EMVS_FUSE_RMS>(ex, d_depths); break;
+        default: rc = launch_band_sweep<EMVS_FUSE_MAX>(ex, d_depths); break;
+      }
+      if (rc) return rc;
+    }
+  } else {
+  ex->epoch++;
   k_flag_signal<<<1, 32, 0, st>>>(ex->flag_ptrs, ex->n_ranks, ex->rank, 0, ex->epoch);   // "my partial DSIs are built"
   ctx->launches++;
   if (row_hi > row_lo) {
@@ -1549,7 +1689,9 @@ int emvs_exchange_fuse_collapse(emvs_exchange* ex, int method, const float* d_de
     }
     if (rc) return rc;
   }
-  k_flag_signal<<<1, 32, 0, st>>>(ex->flag_ptrs, ex->n_ranks, ex->rank, 1, ex->epoch);   // "my band is stored everywhere"
+  }
+  // "done": my peer loads of this round are finished and my band is stored everywhere; then wait for everyone
+  k_flag_signal<<<1, 32, 0, st>>>(ex->flag_ptrs, ex->n_ranks, ex->rank, 1, ex->epoch);
   k_flag_wait<<<1, 32, 0, st>>>(ex->flags, ex->n_ranks, 1, ex->epoch, timeout, ex->flags + 2 * kMaxPeerRanks);
   ctx->launches += 2;
   CUDA_TRY(cudaGetLastError());

@@ -130,10 +130,14 @@ enum {
 enum {
   EMVS_BUILD_RESET = 0,       /* dsi_.resetGrid() then vote (MAP:145-146) — the reference behaviour */
   EMVS_BUILD_ACCUMULATE = 1,  /* vote on top of the current contents (sub-interval sharding)  */
-  EMVS_BUILD_ALLREDUCE = 2    /* multi-GPU: this build is one rank's shard; every Z-slab is summed over
+  EMVS_BUILD_ALLREDUCE = 2,   /* multi-GPU: this build is one rank's shard; every Z-slab is summed over
                                  the ranks (ncclAllReduce) as soon as it is voted, overlapped with the
                                  votes of the next slab; the vote counts are summed too.  Needs
                                  emvs_comm_init; every rank must issue the same sequence of builds.      */
+  EMVS_BUILD_PEER_REDUCE = 4  /* multi-GPU, fused exchange (emvs_exchange_begin ... emvs_exchange_fuse_collapse):
+                                 every Z-slab, once merged, is announced to the peers and this rank's row band of
+                                 it is summed over all ranks straight from their HBM (NVLink peer loads) into a
+                                 local band buffer, on a side stream under the votes of the next slab.           */
 };
 
 typedef struct emvs_context emvs_context;  /* one CUDA device + stream + scratch              */
@@ -280,6 +284,9 @@ EMVS_API int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size
  * Returns EMVS_ERR_TOO_FEW (-> `false`) when n_events < 1024. */
 EMVS_API int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
                              const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w);
+/* emvs_mapper_evaluate_dsi with build flags (EMVS_BUILD_ALLREDUCE / EMVS_BUILD_PEER_REDUCE for a rank's shard). */
+EMVS_API int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                                   const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w, int flags);
 /* Build-defined integer observable: accepted (event, plane k) votes of the last
  * build(s) since the last RESET, one uint64 per plane. */
 EMVS_API int emvs_mapper_counts(const emvs_mapper* m, uint64_t* per_plane /* dimZ */);
@@ -321,6 +328,11 @@ EMVS_API int emvs_exchange_destroy(emvs_exchange* ex);
 EMVS_API int emvs_exchange_blob_bytes(const emvs_exchange* ex, size_t* out);
 EMVS_API int emvs_exchange_export(emvs_exchange* ex, uint8_t* blob);
 EMVS_API int emvs_exchange_import(emvs_exchange* ex, const uint8_t* all_blobs /* n_ranks * blob_bytes */);
+/* Optional overlapped form of a round: emvs_exchange_begin, then build every camera of the exchange with
+ * EMVS_BUILD_PEER_REDUCE (same order on every rank), then emvs_exchange_fuse_collapse, which in that case only
+ * runs a local sweep over the already-reduced band and distributes it.  Without begin, fuse_collapse does the
+ * whole reduction in one exposed sweep after the builds. */
+EMVS_API int emvs_exchange_begin(emvs_exchange* ex);
 /* method: EMVS_FUSE_*; d_depths: DEVICE depth table (emvs_mapper_depths_device) or NULL. */
 EMVS_API int emvs_exchange_fuse_collapse(emvs_exchange* ex, int method, const float* d_depths);
 /* Device pointers of this rank's map buffers (conf f32, idx u8|u16, depth f32; dimY*dimX each). */

@@ -49,12 +49,19 @@ def main():
         packets = [m.packetize(ev, tr, T) for m, ev, tr in zip(mappers, events, trajs)]
         # (a) fused path: partial DSIs stay partial, one sweep over peer memory produces the maps
         ex = api.PeerExchange(ctx, [m.dsi_ for m in mappers], world, rank, allgather)
-        for rep in range(2):   # twice: the epoch flags must work repeatedly
+        peer_results = []
+        for rep in range(4):   # repeated rounds: the epoch flags must keep working; even = one exposed sweep,
+            banded = rep % 2 == 1   # odd = slab-wise band reduce overlapped with voting
+            if banded:
+                ex.begin()
             for cam, lo, hi in shard.plan([len(p) for p in packets], world, rank):
-                mappers[cam].build(events[cam], packets[cam][lo:hi])
+                mappers[cam].build(events[cam], packets[cam][lo:hi], peer_reduce=banded)
             ex.fuse_collapse(method, mappers[0].depths_device_ptr())
-            conf_p, idx_p, depth_p = ex.download()
+            peer_results.append(ex.download())
         ex.close()
+        for r in peer_results[1:]:   # both forms sum the same partial voxels in the same rank order: identical maps
+            assert all(np.array_equal(a, b) for a, b in zip(r, peer_results[0])), "peer sweep forms disagree"
+        conf_p, idx_p, depth_p = peer_results[-1]
         # (b) allreduce paths
         for cam, lo, hi in shard.plan([len(p) for p in packets], world, rank):
             if overlapped:   # EMVS_BUILD_ALLREDUCE: every Z-slab is summed while the next one is voted
