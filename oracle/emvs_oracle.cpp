@@ -4,11 +4,15 @@
 // this file.  Allowed users: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline
 // leg and `bench.py --impl reference`.
 //
-// PARITY UNPINNED: the reference (tub-rip/dvs_mcemvs @ 49fbc7e) ships no tests, golden
-// vectors or fixtures for this path, and it cannot be compiled here (needs ROS/catkin,
-// Eigen, minkindr, OpenCV C++, glog, gflags ...; none installed, no network).  This file
-// restates the reference's loops from its sources; every function cites the lines it
-// follows.  Paths are relative to the reference root; abbreviations:
+// The reference (tub-rip/dvs_mcemvs @ 49fbc7e) ships no tests, golden vectors or fixtures for
+// this path, and as a whole it cannot be compiled here (needs ROS/catkin, Eigen, minkindr,
+// OpenCV C++, glog, gflags ...; none installed, no network).  This file restates the reference's
+// loops from its sources; every function cites the lines it follows.
+// PINNED bit-exactly against the reference's own code compiled in place (oracle/Makefile target
+// `ref`: cartesian3dgrid.{h,cpp}, depth_vector.hpp, median_filtering.cpp) and against cv2:
+// vote(), fuse_op(), collapse_max(), mean_square(), depth_vector(), depth_map_post().
+// PARITY UNPINNED: packetize(), pose_at() and friends, warp_events(), fill_voxel_grid()'s Eq.15
+// expression order (Eigen / minkindr arithmetic of mapper_emvs_stereo.cpp, which cannot be built).  Paths are relative to the reference root; abbreviations:
 //   MAP = mapper_emvs_stereo/src/mapper_emvs_stereo.cpp
 //   G3H = cartesian3dgrid/include/cartesian3dgrid/cartesian3dgrid.h
 //   G3C = cartesian3dgrid/src/cartesian3dgrid.cpp

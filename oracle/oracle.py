@@ -2,9 +2,13 @@
 
 TEST INFRASTRUCTURE ONLY — see the header of emvs_oracle.cpp.  May be imported by tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the
-package.  PARITY UNPINNED: the reference has no golden vectors and cannot be built here; the
-oracle is pinned only by the closed-form known-answer tests in tests/test_oracle_kat.py and
-by agreement between its two independent statements (C++ loops here vs. numpy below).
+package.  Pinning: the Grid3D layer (bilinear vote, all voxel ops, collapseMaxZSlice,
+computeMeanSquare), the depth tables, the masked median and the OpenCV post-processing arithmetic are
+pinned bit-exactly against the reference's own sources compiled in place (oracle/_ref) and against
+cv2 (tests/golden/*.npz, tests/test_oracle_pinned.py, tests/test_depthmap_post.py).  PARITY UNPINNED
+for the packet / event stages of mapper_emvs_stereo.cpp (Eigen + minkindr arithmetic: the mapper
+cannot be compiled here); those are held by the known-answer tests in tests/test_oracle_kat.py and by
+agreement between the two independent statements (C++ loops here vs. numpy below).
 """
 import ctypes as C
 import os
