@@ -23,7 +23,8 @@
 namespace emvs {
 namespace {
 
-// ---- small fixed-size float algebra with Eigen's evaluation order ----------------------------
+// ---- small fixed-size float algebra with Eigen's (>= 3.3) evaluation order --------------------
+// three-term sums are a0 + (a1 + a2): (row .* col).sum() unrolls through redux_novec_unroller with HalfLength = 3/2 = 1
 struct Mat3f {
   float m[3][3];
 };
@@ -33,9 +34,9 @@ inline Mat3f operator*(const Mat3f& a, const Mat3f& b)
   Mat3f r;
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) {
-      float s = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j];
-      s = s + a.m[i][2] * b.m[2][j];
-      r.m[i][j] = s;
+      // Eigen >= 3.3: (row .* col).sum() of three terms unrolls to a0 + (a1 + a2)
+      const float s12 = a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+      r.m[i][j] = a.m[i][0] * b.m[0][j] + s12;
     }
   return r;
 }
@@ -52,8 +53,8 @@ inline Mat3f inverse(const Mat3f& a)
   float cof[3][3];
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) cof[r][c] = minor2(a, r, c);
-  float det = cof[0][0] * a.m[0][0] + cof[1][0] * a.m[1][0];
-  det = det + cof[2][0] * a.m[2][0];
+  const float det12 = cof[1][0] * a.m[1][0] + cof[2][0] * a.m[2][0];
+  const float det = cof[0][0] * a.m[0][0] + det12;
   const float inv_det = 1.f / det;
   Mat3f out;
   for (int r = 0; r < 3; ++r)
@@ -337,8 +338,8 @@ size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose
     emvs_packet& pk = out[produced++];
     pk.first_event = cur;
     for (int i = 0; i < 3; ++i) {  // C = -R^T t
-      float s = (-R.m[0][i]) * t[0] + (-R.m[1][i]) * t[1];
-      pk.C[i] = s + (-R.m[2][i]) * t[2];
+      const float s12 = (-R.m[1][i]) * t[1] + (-R.m[2][i]) * t[2];
+      pk.C[i] = (-R.m[0][i]) * t[0] + s12;
     }
     Mat3f Hinv = R;  // (H_z0)^-1 = z0 R + t e3^T
     for (int i = 0; i < 3; ++i)

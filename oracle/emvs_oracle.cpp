@@ -92,16 +92,19 @@ static void depth_vector(int inverse, float min_depth, float max_depth, size_t n
 
 // ---------------------------------------------------------------------------------------
 // Eigen-style fixed-size float 3x3 helpers (row-major storage m[3*r+c]).
-// Product coefficient = ((a0*b0 + a1*b1) + a2*b2); inverse = cofactor / determinant with
-// det = sum(cofactor column 0 * matrix column 0) and a single reciprocal, as Eigen's
-// compute_inverse<Matrix3f> does.
+// Eigen >= 3.3 evaluates a coefficient of a small fixed-size product as
+// (lhs.row(i).cwiseProduct(rhs.col(j))).sum(), and sum() of THREE terms unrolls (redux_novec_unroller,
+// HalfLength = 3/2 = 1) to a0 + (a1 + a2); four terms give (a0 + a1) + (a2 + a3).  The 3x3 inverse is
+// cofactor / determinant with det = (cofactor column 0 .* matrix column 0).sum() — again a0 + (a1 + a2) —
+// and a single reciprocal (compute_inverse_size3_helper).  Eigen is not part of the reference tree, so this
+// order is restated from Eigen's sources, not checkable here (parity unpinned).
 // ---------------------------------------------------------------------------------------
 static void mat3_mul(const float* a, const float* b, float* out)
 {
   float r[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j)
-      r[3 * i + j] = (a[3 * i + 0] * b[0 + j] + a[3 * i + 1] * b[3 + j]) + a[3 * i + 2] * b[6 + j];
+      r[3 * i + j] = a[3 * i + 0] * b[0 + j] + (a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j]);
   std::memcpy(out, r, sizeof r);
 }
 
@@ -114,7 +117,7 @@ static inline float cof3(const float* m, int i, int j)
 static void mat3_inv(const float* m, float* out)
 {
   const float c0 = cof3(m, 0, 0), c1 = cof3(m, 1, 0), c2 = cof3(m, 2, 0);
-  const float det = (c0 * m[0] + c1 * m[3]) + c2 * m[6];
+  const float det = c0 * m[0] + (c1 * m[3] + c2 * m[6]);
   const float invdet = 1.f / det;
   float r[9];
   r[0] = c0 * invdet; r[1] = c1 * invdet; r[2] = c2 * invdet;
@@ -299,7 +302,7 @@ static size_t packetize(const Event* ev, size_t n_ev,
     Packet& p = out[n_out++];
     p.first_event = cur;
     for (int i = 0; i < 3; ++i)                                       // MAP:108  -R^T t
-      p.C[i] = ((-R[0 + i]) * t[0] + (-R[3 + i]) * t[1]) + (-R[6 + i]) * t[2];
+      p.C[i] = (-R[0 + i]) * t[0] + ((-R[3 + i]) * t[1] + (-R[6 + i]) * t[2]);
     float Hinv[9];
     for (int i = 0; i < 9; ++i) Hinv[i] = R[i] * z0;                  // MAP:114-115
     Hinv[2] += t[0]; Hinv[5] += t[1]; Hinv[8] += t[2];                // MAP:116
