@@ -148,6 +148,7 @@ def cpu_reference(args, n_full):
     loop is linear in the event count; fusion and argmax do not depend on it) and converts to the
     full workload: t_full = t_build * n_full / n_sample + t_fuse + t_argmax."""
     from oracle import oracle as O
+    O.use_all_host_threads()   # torchrun sets OMP_NUM_THREADS=1 for its workers; the baseline gets every host thread
     n_s = min(args.cpu_sample_events, n_full)
     if (n_s, args.kind) not in _CPU_WORKLOAD:      # synthetic input generation is not part of any timed scope
         _CPU_WORKLOAD[(n_s, args.kind)] = make_workload(n_s, 0, args.kind)

@@ -652,6 +652,16 @@ int oracle_depth_map_post(float* conf, const uint8_t* idx, int rows, int cols, i
                           int median_size, const float* depths, uint8_t* conf8, uint8_t* mask, uint8_t* idx_filtered, float* depth)
 { return oracle::depth_map_post(conf, idx, rows, cols, ks, c, max_confidence, median_size, depths, conf8, mask, idx_filtered, depth); }
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must still use every host thread.
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -214,6 +214,13 @@ def num_threads():
     return lib().oracle_num_threads()
 
 
+def use_all_host_threads():
+    """OpenMP team size = the CPUs this process may run on (overrides an OMP_NUM_THREADS=1 set by torchrun)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 # ---- numpy twin (independent second statement, small cases only) -------------------------------
 def np_build_dsi(xy0, packets, depths, virt4, dimX, dimY):
     """fillVoxelGrid (mapper_emvs_stereo.cpp:151-205) + vote (cartesian3dgrid.h:253-273) with numpy
