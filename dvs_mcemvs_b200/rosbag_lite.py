@@ -1,0 +1,191 @@
+"""Minimal ROS bag (format 2.0, uncompressed chunks) reader / writer for the two message types the
+mapping path consumes — no ROS installation needed.
+
+  geometry_msgs/PoseStamped  -> STAMPED_POSE_DTYPE control poses (what parse_rosbag_gt collects,
+                                mapper_emvs_stereo/src/data_loading.cpp:305-465; the bundled
+                                data/DSEC/*/pose.bag files are exactly this)
+  dvs_msgs/EventArray        -> EVENT_DTYPE events (data_loading.cpp:33-219); a serialised
+                                dvs_msgs/Event is 13 bytes {uint16 x, uint16 y, time ts, bool polarity},
+                                the in-memory struct the engine takes is the 16-byte padded one
+
+The writer exists so that tests can round-trip synthetic streams; it emits one uncompressed chunk per
+call plus the index records rosbag tools expect.  bz2 / lz4 chunk compression is not supported.
+"""
+import struct
+
+import numpy as np
+
+from ._capi import EVENT_DTYPE, STAMPED_POSE_DTYPE
+
+MAGIC = b"#ROSBAG V2.0\n"
+OP_MSG, OP_BAG_HEADER, OP_INDEX, OP_CHUNK, OP_CHUNK_INFO, OP_CONNECTION = 2, 3, 4, 5, 6, 7
+
+
+# ---- record level ----------------------------------------------------------------------------------
+def _parse_header(buf):
+    fields, o = {}, 0
+    while o < len(buf):
+        (n,) = struct.unpack_from("<I", buf, o)
+        o += 4
+        k, v = bytes(buf[o:o + n]).split(b"=", 1)
+        fields[k.decode()] = v
+        o += n
+    return fields
+
+
+def _records(buf, start, end):
+    o = start
+    while o < end:
+        (hl,) = struct.unpack_from("<I", buf, o)
+        hdr = _parse_header(buf[o + 4:o + 4 + hl])
+        o += 4 + hl
+        (dl,) = struct.unpack_from("<I", buf, o)
+        yield hdr, o + 4, dl
+        o += 4 + dl
+
+
+def read_messages(path, topics=None, types=None):
+    """Yields (topic, msg_type, receive_time(sec, nsec), payload memoryview) in file order."""
+    buf = memoryview(open(path, "rb").read())
+    if bytes(buf[:len(MAGIC)]) != MAGIC:
+        raise ValueError(f"{path}: not a ROS bag v2.0")
+    conns = {}
+
+    def handle(hdr, off, n, base):
+        op = hdr["op"][0]
+        if op == OP_CONNECTION:
+            info = _parse_header(base[off:off + n])
+            conns[struct.unpack("<I", hdr["conn"])[0]] = (hdr["topic"].decode(), info["type"].decode())
+        elif op == OP_MSG:
+            topic, mtype = conns[struct.unpack("<I", hdr["conn"])[0]]
+            if (topics is None or topic in topics) and (types is None or mtype in types):
+                return topic, mtype, struct.unpack("<II", hdr["time"]), base[off:off + n]
+        return None
+
+    for hdr, off, n in _records(buf, len(MAGIC), len(buf)):
+        op = hdr["op"][0]
+        if op == OP_CHUNK:
+            if hdr["compression"] != b"none":
+                raise NotImplementedError(f"{path}: {hdr['compression'].decode()} chunks are not supported")
+            for h2, o2, n2 in _records(buf, off, off + n):
+                m = handle(h2, o2, n2, buf)
+                if m:
+                    yield m
+        else:
+            m = handle(hdr, off, n, buf)
+            if m:
+                yield m
+
+
+# ---- message level ---------------------------------------------------------------------------------
+def _skip_std_header(p, o=0):
+    """std_msgs/Header {uint32 seq; time stamp; string frame_id} -> (stamp(sec, nsec), offset after it)."""
+    _, sec, nsec, flen = struct.unpack_from("<IIII", p, o)
+    return (sec, nsec), o + 16 + flen
+
+
+def read_poses(path, topic=None):
+    """All geometry_msgs/PoseStamped messages [of `topic`] as STAMPED_POSE_DTYPE, sorted by header stamp
+    (the std::map<ros::Time, Transformation> ordering of the reference; later duplicates of a stamp win)."""
+    out = {}
+    for _, _, _, p in read_messages(path, topics=None if topic is None else {topic}, types={"geometry_msgs/PoseStamped"}):
+        stamp, o = _skip_std_header(p)
+        px, py, pz, qx, qy, qz, qw = struct.unpack_from("<7d", p, o)
+        out[stamp] = ((qw, qx, qy, qz), (px, py, pz))
+    arr = np.zeros(len(out), STAMPED_POSE_DTYPE)
+    for i, stamp in enumerate(sorted(out)):
+        arr["sec"][i], arr["nsec"][i] = stamp
+        arr["T"]["q"][i], arr["T"]["t"][i] = out[stamp]
+    return arr
+
+
+_EV_WIRE = np.dtype([("x", "<u2"), ("y", "<u2"), ("sec", "<u4"), ("nsec", "<u4"), ("polarity", "u1")])   # 13 bytes, packed
+assert _EV_WIRE.itemsize == 13
+
+
+def read_events(path, topic=None, t_min=None, t_max=None, sort=True):
+    """All dvs_msgs/EventArray messages [of `topic`] concatenated as EVENT_DTYPE, optionally restricted to
+    t_min <= t < t_max (seconds) and sorted by timestamp like parse_rosbag does (data_loading.cpp:196-214)."""
+    parts = []
+    for _, _, _, p in read_messages(path, topics=None if topic is None else {topic}, types={"dvs_msgs/EventArray"}):
+        _, o = _skip_std_header(p)
+        _, _, n = struct.unpack_from("<III", p, o)   # height, width, events.size()
+        parts.append(np.frombuffer(p, _EV_WIRE, count=n, offset=o + 12))
+    wire = np.concatenate(parts) if parts else np.zeros(0, _EV_WIRE)
+    ev = np.zeros(wire.shape[0], EVENT_DTYPE)
+    for f in ("x", "y", "sec", "nsec", "polarity"):
+        ev[f] = wire[f]
+    t = ev["sec"].astype(np.float64) + 1e-9 * ev["nsec"]
+    keep = np.ones(ev.shape[0], bool)
+    if t_min is not None:
+        keep &= t >= t_min
+    if t_max is not None:
+        keep &= t < t_max
+    ev, t = ev[keep], t[keep]
+    if sort:
+        key = ev["sec"].astype(np.uint64) * np.uint64(1_000_000_000) + ev["nsec"].astype(np.uint64)
+        ev = ev[np.argsort(key, kind="stable")]
+    return ev
+
+
+# ---- writer (tests / synthetic data) ------------------------------------------------------------------
+def _hdr(**fields):
+    b = b"".join(struct.pack("<I", len(k) + 1 + len(v)) + k.encode() + b"=" + v for k, v in fields.items())
+    return struct.pack("<I", len(b)) + b
+
+
+def _record(header, data):
+    return header + struct.pack("<I", len(data)) + data
+
+
+def _std_header(seq, sec, nsec, frame_id=b""):
+    return struct.pack("<IIII", seq, sec, nsec, len(frame_id)) + frame_id
+
+
+def write_bag(path, poses=None, pose_topic="/pose", events=None, event_topic="/dvs/events", sensor=(640, 480),
+              events_per_message=5000):
+    """Writes one bag holding the given control poses (STAMPED_POSE_DTYPE) and / or events (EVENT_DTYPE)."""
+    conns, msgs = [], []   # msgs: (conn id, (sec, nsec), payload)
+    if poses is not None:
+        cid = len(conns)
+        conns.append((pose_topic, "geometry_msgs/PoseStamped", "d3812c3cbc69362b77dc0b19b345f8f5"))
+        for i, p in enumerate(np.asarray(poses, STAMPED_POSE_DTYPE)):
+            q, t = p["T"]["q"], p["T"]["t"]
+            msgs.append((cid, (int(p["sec"]), int(p["nsec"])), _std_header(i, int(p["sec"]), int(p["nsec"])) +
+                         struct.pack("<7d", t[0], t[1], t[2], q[1], q[2], q[3], q[0])))
+    if events is not None:
+        cid = len(conns)
+        conns.append((event_topic, "dvs_msgs/EventArray", "5e8beee5a6c107e504c2e78903c224b8"))
+        ev = np.asarray(events, EVENT_DTYPE)
+        for i, s in enumerate(range(0, len(ev), events_per_message)):
+            e = ev[s:s + events_per_message]
+            wire = np.zeros(len(e), _EV_WIRE)
+            for f in ("x", "y", "sec", "nsec", "polarity"):
+                wire[f] = e[f]
+            stamp = (int(e["sec"][-1]), int(e["nsec"][-1]))
+            msgs.append((cid, stamp, _std_header(i, *stamp) + struct.pack("<III", sensor[1], sensor[0], len(e)) + wire.tobytes()))
+    msgs.sort(key=lambda m: m[1])
+    conn_recs = [_record(_hdr(op=bytes([OP_CONNECTION]), conn=struct.pack("<I", c), topic=t.encode()),
+                         _hdr(topic=t.encode(), type=ty.encode(), md5sum=md5.encode(), message_definition=b"")[4:])
+                 for c, (t, ty, md5) in enumerate(conns)]
+    chunk, index = b"".join(conn_recs), {c: [] for c in range(len(conns))}
+    for c, stamp, payload in msgs:
+        index[c].append((stamp, len(chunk)))
+        chunk += _record(_hdr(op=bytes([OP_MSG]), conn=struct.pack("<I", c), time=struct.pack("<II", *stamp)), payload)
+    chunk_pos = len(MAGIC) + 4096
+    body = _record(_hdr(op=bytes([OP_CHUNK]), compression=b"none", size=struct.pack("<I", len(chunk))), chunk)
+    for c, entries in index.items():
+        body += _record(_hdr(op=bytes([OP_INDEX]), ver=struct.pack("<I", 1), conn=struct.pack("<I", c),
+                             count=struct.pack("<I", len(entries))),
+                        b"".join(struct.pack("<III", s[0], s[1], off) for s, off in entries))
+    index_pos = chunk_pos + len(body)
+    t0, t1 = (msgs[0][1], msgs[-1][1]) if msgs else ((0, 0), (0, 0))
+    tail = b"".join(conn_recs) + _record(
+        _hdr(op=bytes([OP_CHUNK_INFO]), ver=struct.pack("<I", 1), chunk_pos=struct.pack("<Q", chunk_pos),
+             start_time=struct.pack("<II", *t0), end_time=struct.pack("<II", *t1), count=struct.pack("<I", len(conns))),
+        b"".join(struct.pack("<II", c, len(e)) for c, e in index.items()))
+    bag_hdr = _hdr(op=bytes([OP_BAG_HEADER]), index_pos=struct.pack("<Q", index_pos), conn_count=struct.pack("<I", len(conns)),
+                   chunk_count=struct.pack("<I", 1))
+    pad = 4096 - len(bag_hdr) - 4
+    with open(path, "wb") as f:
+        f.write(MAGIC + bag_hdr + struct.pack("<I", pad) + b" " * pad + body + tail)
