@@ -281,13 +281,16 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       if (ncclAllReduce_checked(nccl, ctx, g->d, g->n_cells, st)) return EMVS_ERR_NCCL;
       if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, g->dimZ, st)) return EMVS_ERR_NCCL;
     }
-    if (peer) {    // an all-zero partial DSI: one "slab" covering every plane
-      const int rc = peer_reduce_slab(ctx, ex, peer_cam, 0, 0, g->dimZ, st);
-      if (rc) return rc;   // (emvs_exchange_fuse_collapse waits for the communication stream)
+    if (peer) {    // an all-zero partial DSI: announce and reduce the same slabs as the ranks that do vote
+      const uint32_t zslab = choose_slab(ctx, g->dimX, g->dimY, g->dimZ);
+      for (uint32_t k0 = 0; k0 < g->dimZ; k0 += zslab) {
+        const int rc = peer_reduce_slab(ctx, ex, peer_cam, k0 / zslab, k0, std::min(zslab, g->dimZ - k0), st);
+        if (rc) return rc;   // (emvs_exchange_fuse_collapse waits for the communication stream)
+      }
     }
     return EMVS_OK;
   }
-  (void)n_events;
+  (void)n_events;   // the packets carry the event indices; n_events is validated by the host-buffer entry points
   const size_t n_voted = n_packets * (size_t)EMVS_PACKET_SIZE;
   {
     const int rc = grow((void**)&ctx->d_xy0, &ctx->xy0_cap, n_voted * sizeof(float2));
@@ -1516,8 +1519,6 @@ int emvs_exchange_import(emvs_exchange* ex, const uint8_t* all)
   REQUIRE(!ex->imported, EMVS_ERR_STATE, "exchange_import: already imported");
   DeviceGuard guard(ex->ctx->device);
   const size_t per_rank = kIpcBytes * (size_t)(ex->n_cams + 2);
-  const size_t n_pix = (size_t)ex->dimX * ex->dimY;
-  (void)n_pix;
   PeerArgs& A = ex->args;
   A.n_cams = ex->n_cams;
   A.n_ranks = ex->n_ranks;
