@@ -277,8 +277,13 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   }
   if (n_packets == 0) {
     if (!accumulate) CUDA_TRY(cudaMemsetAsync(g->d, 0, g->n_cells * sizeof(float), st));
-    if (reduce) {  // this rank has no packets but must still take part in the collective
-      if (ncclAllReduce_checked(nccl, ctx, g->d, g->n_cells, st)) return EMVS_ERR_NCCL;
+    if (reduce) {  // this rank has no packets but must issue the SAME sequence of collectives as the others
+      const uint32_t zslab = choose_slab(ctx, g->dimX, g->dimY, g->dimZ);
+      const size_t plane = (size_t)g->dimX * g->dimY;
+      for (uint32_t k0 = 0; k0 < g->dimZ; k0 += zslab) {
+        const uint32_t nk = std::min(zslab, g->dimZ - k0);
+        if (ncclAllReduce_checked(nccl, ctx, g->d + (size_t)k0 * plane, (size_t)nk * plane, st)) return EMVS_ERR_NCCL;
+      }
       if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, g->dimZ, st)) return EMVS_ERR_NCCL;
     }
     if (peer) {    // an all-zero partial DSI: announce and reduce the same slabs as the ranks that do vote
