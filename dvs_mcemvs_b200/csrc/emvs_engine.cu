@@ -304,10 +304,11 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   const uint32_t dimX = g->dimX, dimY = g->dimY, dimZ = g->dimZ;
   const uint32_t QW = ceil_div(dimX, 2), QH = ceil_div(dimY, 2);
   const uint32_t slab = choose_slab(ctx, dimX, dimY, dimZ);
-  // plane-paired scratch layout + k_vote_paired (EMVS_VOTE_PAIR=0 selects the plain one-plane-per-instruction kernel)
-  static const bool pair_env = [] { const char* e = getenv("EMVS_VOTE_PAIR"); return e ? atoi(e) != 0 : true; }();
-  const bool paired = pair_env;
-  const size_t slab_bytes = (size_t)((slab + 1) / 2 * 2) * QW * QH * 4 * sizeof(float4);
+  // plane-grouped scratch layout + k_vote_grouped<G> (EMVS_VOTE_GROUP=1 selects the plain one-plane-per-instruction kernel)
+  static const uint32_t group_env = [] { const char* e = getenv("EMVS_VOTE_GROUP"); const int g = e ? atoi(e) : 2; return (uint32_t)(g == 4 ? 4 : g == 1 ? 1 : 2); }();
+  const uint32_t G = group_env;
+  auto round_up_g = [&](uint32_t n) { return (n + G - 1) / G * G; };
+  const size_t slab_bytes = (size_t)round_up_g(slab) * QW * QH * 4 * sizeof(float4);
   const bool overlap = ctx->overlap;
   for (int b = 0; b < (overlap ? 2 : 1); ++b) {
     const int rc = ensure_quad(ctx, b, slab_bytes);
@@ -355,9 +356,12 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       ctx->prof_used += 2;
       CUDA_TRY(cudaEventRecord(pe0, st));
     }
-    if (paired)
-      k_vote_paired<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
-                                                                     m->d_counts);
+    if (G == 2)
+      k_vote_grouped<2><<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
+                                                                         m->d_counts);
+    else if (G == 4)
+      k_vote_grouped<4><<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
+                                                                         m->d_counts);
     else
       k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
                                                               m->d_counts);
@@ -369,9 +373,9 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
     }
     dim3 mb(32, 8, 1), mg(ceil_div(QW, 32), ceil_div(QH, 8), nk);
     k_merge_quads<<<mg, mb, 0, ms>>>(ctx->quad[b], g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
-                                     accumulate ? 1 : 0, paired ? 1 : 0);
+                                     accumulate ? 1 : 0, (int)G);
     ctx->launches++;
-    CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, (size_t)((nk + 1) / 2 * 2) * QW * QH * 4 * sizeof(float4), ms));
+    CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, (size_t)round_up_g(nk) * QW * QH * 4 * sizeof(float4), ms));
     if (overlap) {
       CUDA_TRY(cudaEventRecord(ctx->ev_merge[b], ms));
       ctx->merge_pending[b] = true;
