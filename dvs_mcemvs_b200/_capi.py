@@ -63,6 +63,7 @@ _PROTOTYPES = {
     "emvs_context_destroy": (C.c_int, [_vp]),
     "emvs_context_sync": (C.c_int, [_vp]),
     "emvs_context_set_slab": (C.c_int, [_vp, C.c_uint32]),
+    "emvs_context_set_upload_split": (C.c_int, [_vp, C.c_uint32, C.c_uint64]),
     "emvs_context_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "emvs_context_profile_vote": (C.c_int, [_vp, C.c_int]),
     "emvs_context_vote_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -82,6 +83,8 @@ _PROTOTYPES = {
     "emvs_pose_inverse": (C.c_int, [_vp, _vp]),
     "emvs_packetize": (C.c_int, [_vp, _sz, _vp, _sz, _vp, C.POINTER(Camera), _vp, C.c_float, _vp, _sz,
                                  C.POINTER(_sz)]),
+    "emvs_packetize_range": (C.c_int, [_vp, _sz, _vp, _sz, _vp, C.POINTER(Camera), _vp, C.c_float, C.POINTER(_sz), _sz,
+                                       _vp, _sz, C.POINTER(_sz)]),
     "emvs_grid_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
     "emvs_grid_destroy": (C.c_int, [_vp]),
     "emvs_grid_dims": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

@@ -138,6 +138,10 @@ class Context:
     def set_slab(self, planes):
         check(_lib().emvs_context_set_slab(self._h, int(planes)))
 
+    def set_upload_split(self, percent, min_events=1 << 20):
+        """evaluateDSI on an idle pipeline votes the first `percent` % of the events while the rest is uploaded."""
+        check(_lib().emvs_context_set_upload_split(self._h, int(percent), int(min_events)))
+
     def launch_count(self):
         n = C.c_uint64(0)
         check(_lib().emvs_context_launch_count(self._h, C.byref(n)))
@@ -463,6 +467,20 @@ class MapperEMVS:
             return None
         check(rc)
         return out[:n_pk.value]
+
+    def packetize_range(self, events, trajectory, T_rv_w, cursor, event_limit):
+        """Resumable packet stage: packets that fit in events[:event_limit], continuing at event `cursor`.
+        Returns (packets, new cursor)."""
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        n = events.shape[0]
+        out = np.zeros(n // capi.PACKET_SIZE + 1, dtype=PACKET_DTYPE)
+        n_pk, cur = C.c_size_t(0), C.c_size_t(int(cursor))
+        cs = self.cam.c_struct()
+        check(_lib().emvs_packetize_range(ptr(events), n, ptr(trajectory.poses), trajectory.poses.shape[0],
+                                          ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE)), C.byref(cs),
+                                          ptr(self.virtual_cam_), float(self.raw_depths_vec_[0]), C.byref(cur),
+                                          int(event_limit), ptr(out), out.shape[0], C.byref(n_pk)))
+        return out[:n_pk.value], cur.value
 
     def evaluateDSI(self, events, trajectory, T_rv_w, allreduce=False, peer_reduce=False):
         """bool evaluateDSI(events, trajectory, T_rv_w) — mapper_emvs_stereo.cpp:67-148.

@@ -88,6 +88,10 @@ struct emvs_context {
   double* d_partial = nullptr;                        // 1024 partial sums + 1 result
   // pinned host staging for packets produced by evaluate_dsi
   emvs_packet* h_packets = nullptr; size_t h_packets_cap = 0;
+  // evaluate_dsi on an idle pipeline: the head of the event list (split_percent %) is uploaded and voted first
+  // while the tail is still crossing PCIe (see emvs_mapper_evaluate_dsi_flags); 0 disables
+  uint32_t split_percent = 25;
+  size_t split_min_events = (size_t)1 << 20;
   // NCCL
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -556,6 +560,7 @@ int emvs_context_create(int device, emvs_context** out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_merge[b], cudaEventDisableTiming);
   }
   if (const char* env = getenv("EMVS_OVERLAP")) ctx->overlap = atoi(env) != 0;
+  if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_partial, sizeof(double) * 1025);
@@ -625,6 +630,15 @@ int emvs_context_set_slab(emvs_context* ctx, uint32_t planes)
 {
   REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
   ctx->slab_override = planes;
+  return EMVS_OK;
+}
+
+int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t min_events)
+{
+  REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
+  REQUIRE(percent <= 90, EMVS_ERR_INVALID, "set_upload_split: percent must be 0..90");
+  ctx->split_percent = percent;
+  ctx->split_min_events = (size_t)min_events;
   return EMVS_OK;
 }
 
@@ -809,6 +823,19 @@ int emvs_packetize(const emvs_event* events, size_t n_events, const emvs_stamped
 }
 
 // ---- Grid3D ----------------------------------------------------------------------------------
+int emvs_packetize_range(const emvs_event* events, size_t n_events, const emvs_stamped_pose* traj, size_t n_poses,
+                         const emvs_pose* T_rv_w, const emvs_camera* cam, const float virt[4], float z0, size_t* cursor,
+                         size_t event_limit, emvs_packet* out, size_t max_packets, size_t* n_packets)
+{
+  REQUIRE(events && traj && T_rv_w && cam && virt && n_packets && cursor, EMVS_ERR_INVALID, "packetize_range: NULL argument");
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  REQUIRE(event_limit <= n_events && *cursor <= n_events, EMVS_ERR_INVALID, "packetize_range: cursor / limit past the list");
+  REQUIRE(out || max_packets == 0, EMVS_ERR_INVALID, "packetize_range: out is NULL");
+  *n_packets = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, *cam, virt, z0, cursor, event_limit, out,
+                                    max_packets);
+  return EMVS_OK;
+}
+
 int emvs_grid_create(emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ, emvs_grid** out)
 {
   REQUIRE(ctx && out, EMVS_ERR_INVALID, "grid_create: NULL argument");
@@ -1238,8 +1265,11 @@ static int upload_events(emvs_context* ctx, const emvs_event* events, size_t n_e
   return EMVS_OK;
 }
 
+// tail_lo < tail_hi: events [tail_lo, tail_hi) are enqueued for upload right after this build's packets and before
+// its kernels are launched (split upload of emvs_mapper_evaluate_dsi_flags: the copy engine never idles while the
+// host launches the head's kernels).
 static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
-                           size_t n_packets, int flags, bool events_uploaded)
+                           size_t n_packets, int flags, bool events_uploaded, size_t tail_lo = 0, size_t tail_hi = 0)
 {
   emvs_context* ctx = m->ctx;
   const unsigned par = ctx->build_parity++ & 1u;
@@ -1253,13 +1283,18 @@ static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_ev
       const int rc = upload_events(ctx, events, n_events, lo, last);
       if (rc) return rc;
     }
-    const int rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par], n_packets * sizeof(emvs_packet));
+    // sized for the whole list so that head / tail / whole-list builds alternating over the two buffers never regrow them
+    const int rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par],
+                        std::max(n_packets, n_events / EMVS_PACKET_SIZE + 1) * sizeof(emvs_packet));
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], packets, n_packets * sizeof(emvs_packet), cudaMemcpyHostToDevice,
                              ctx->copy_stream));
     CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
   }
+  if (tail_hi > tail_lo)
+    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + tail_lo, events + tail_lo, (tail_hi - tail_lo) * sizeof(emvs_event),
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
   ctx->mark_consumed = true;
   const int rc = build_on_device(m, (const emvs_event*)ctx->d_events, n_events, (const emvs_packet*)ctx->d_packets[par],
                                  n_packets, flags);
@@ -1317,9 +1352,52 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
     ctx->h_packets_cap = max_pk;
   }
   REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi: rectification LUT not set (emvs_mapper_set_lut)");
+  // Split upload.  When the pipeline is idle nothing hides this call's event upload (80 MB per 5 M events, ~1.6 ms
+  // over PCIe 5): upload and vote the HEAD of the list first (a build of its packets), and let the TAIL cross
+  // PCIe under the head's vote kernels; the tail is then voted with EMVS_BUILD_ACCUMULATE into the same DSI
+  // (voting is a sum over events, so head + tail == whole list up to float summation order; the per-plane
+  // counters add exactly).  When the stream is busy (the previous camera is still voting) the whole upload is
+  // already hidden and the list is built in one piece.  The slab-wise exchanges need final slabs: no split.
+  const bool exchange = (flags & (EMVS_BUILD_ALLREDUCE | EMVS_BUILD_PEER_REDUCE)) != 0;
+  size_t n_head = 0;
+  if (ctx->split_percent && !exchange && n_events >= ctx->split_min_events && n_events >= 4 * (size_t)EMVS_PACKET_SIZE) {
+    const cudaError_t q = cudaStreamQuery(ctx->stream);
+    if (q == cudaSuccess) n_head = (n_events / 100 * ctx->split_percent) / EMVS_PACKET_SIZE * EMVS_PACKET_SIZE;
+    else if (q != cudaErrorNotReady) CUDA_TRY(q);
+  }
+  int rc;
+  if (n_head >= EMVS_PACKET_SIZE) {
+    rc = upload_events(ctx, events, n_events, 0, n_head);
+    if (rc) return rc;
+    size_t cur = 0;
+    const size_t n_pk_head = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
+                                                  &cur, n_head, ctx->h_packets, max_pk);
+    if (n_pk_head) {
+      rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk_head, flags, true, n_head, n_events);
+      if (rc) return rc;
+      const size_t n_pk_tail = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
+                                                    &cur, n_events, ctx->h_packets + n_pk_head, max_pk - n_pk_head);
+      if (n_pk_tail) {
+        rc = build_from_host(m, events, n_events, ctx->h_packets + n_pk_head, n_pk_tail, flags | EMVS_BUILD_ACCUMULATE, true);
+        if (rc) return rc;
+      } else {
+        CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse `events` on return
+      }
+      return EMVS_OK;
+    }
+    // no packet in the head (every pose lookup missed): upload the rest and build in one piece
+    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + n_head, events + n_head, (n_events - n_head) * sizeof(emvs_event),
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+    const size_t n_pk = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
+                                             n_events, ctx->h_packets, max_pk);
+    rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, flags, true);
+    if (rc) return rc;
+    if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    return EMVS_OK;
+  }
   // start the event upload first: the host packet stage (one pose + one 3x3 inverse per 1024
   // events) then runs while the copy engine is busy
-  int rc = upload_events(ctx, events, n_events, 0, n_events);
+  rc = upload_events(ctx, events, n_events, 0, n_events);
   if (rc) return rc;
   const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
                                      ctx->h_packets, max_pk);

@@ -23,6 +23,9 @@ int host_rectify_lut(int model, const double K[9], const double* D, int n_d, con
 size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
                       const emvs_pose& T_rv_w, const emvs_camera& cam, const float virt[4], float z0,
                       emvs_packet* out, size_t max_out);
+size_t host_packetize_range(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+                            const emvs_pose& T_rv_w, const emvs_camera& cam, const float virt[4], float z0,
+                            size_t* cur_inout, size_t event_limit, emvs_packet* out, size_t max_out);
 
 // nccl_dl.cpp — NCCL resolved at run time so the library loads (and every single-GPU entry
 // point works) on machines without NCCL, and shares torch's NCCL when loaded from Python.

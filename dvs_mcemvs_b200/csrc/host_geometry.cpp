@@ -315,12 +315,23 @@ size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose
                       const emvs_pose& T_rv_w_pod, const emvs_camera& cam, const float virt[4], float z0,
                       emvs_packet* out, size_t max_out)
 {
+  size_t cur = 0;
+  return host_packetize_range(ev, n_ev, traj, n_poses, T_rv_w_pod, cam, virt, z0, &cur, n_ev, out, max_out);
+}
+
+// Resumable form: continues the packet loop of mapper_emvs_stereo.cpp:86-126 from *cur and stops before the first
+// packet that would reach past `event_limit` (or past the list, strict '<' as :88).  Calling it with growing
+// limits produces exactly the packets of one call over the whole list.
+size_t host_packetize_range(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+                            const emvs_pose& T_rv_w_pod, const emvs_camera& cam, const float virt[4], float z0,
+                            size_t* cur_inout, size_t event_limit, emvs_packet* out, size_t max_out)
+{
   const Mat3f K = pinhole_K(cam.fx, cam.fy, cam.cx, cam.cy);
   const Mat3f Kinv_virtual = inverse(pinhole_K(virt[0], virt[1], virt[2], virt[3]));
   const SE3 T_rv_w = load(T_rv_w_pod);
   size_t produced = 0;
-  size_t cur = 0;
-  while (cur + EMVS_PACKET_SIZE < n_ev && produced < max_out) {
+  size_t cur = *cur_inout;
+  while (cur + EMVS_PACKET_SIZE < n_ev && cur + EMVS_PACKET_SIZE <= event_limit && produced < max_out) {
     const emvs_event& mid = ev[cur + EMVS_PACKET_SIZE / 2];
     SE3 T_w_ev;
     if (!interpolate(traj, n_poses, mid.sec, mid.nsec, &T_w_ev)) {
@@ -349,6 +360,7 @@ size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose
     std::memcpy(pk.H, H.m, sizeof pk.H);
     cur += EMVS_PACKET_SIZE;
   }
+  *cur_inout = cur;
   return produced;
 }
 

@@ -84,6 +84,8 @@ class Grid3D {
   }
 
   void resetGrid() { touch(); emvs_host::check(emvs_grid_reset(g_), "resetGrid"); }
+  // resetGrid() + addTwoGrids(src) in one device copy (the reference's idiom for "initialise with", process1.cpp:126-127)
+  void copyFrom(const Grid3D& src) { touch(); emvs_host::check(emvs_grid_copy(g_, src.g_), "Grid3D::copyFrom"); }
 
   // voxel-wise operations, cartesian3dgrid.h:64-192
   void addTwoGrids(const Grid3D& grid2) { op(grid2, EMVS_OP_ADD, 0, 0.f); }

@@ -177,11 +177,17 @@ class MapperEMVS {
   bool evaluateDSI(const std::vector<emvs_event>& events, const TrajectoryType& trajectory,
                    const geometry_utils::Transformation& T_rv_w)
   {
+    return evaluateDSI(events.data(), events.size(), trajectory, T_rv_w);
+  }
+  // Same on a borrowed range (process_2 / process_5 hand over sub-intervals of one list without copying them).
+  bool evaluateDSI(const emvs_event* events, size_t n_events, const TrajectoryType& trajectory,
+                   const geometry_utils::Transformation& T_rv_w)
+  {
     dsi_.touch();
-    const int rc = emvs_mapper_evaluate_dsi(m_, events.data(), events.size(), trajectory.pods().data(),
-                                            trajectory.pods().size(), &T_rv_w.pod());
+    const int rc = emvs_mapper_evaluate_dsi(m_, events, n_events, trajectory.pods().data(), trajectory.pods().size(),
+                                            &T_rv_w.pod());
     if (rc == EMVS_ERR_TOO_FEW) {
-      std::cerr << "Number of events ( " << events.size() << ") < packet size (" << EMVS_PACKET_SIZE << ")" << std::endl;
+      std::cerr << "Number of events ( " << n_events << ") < packet size (" << EMVS_PACKET_SIZE << ")" << std::endl;
       return false;  // mapper_emvs_stereo.cpp:71-75
     }
     emvs_host::check(rc, "evaluateDSI");

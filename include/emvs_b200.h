@@ -154,6 +154,11 @@ EMVS_API int emvs_context_destroy(emvs_context* ctx);
 EMVS_API int emvs_context_sync(emvs_context* ctx);
 /* Tuning: number of Z-planes voted per pass over the event list (0 = automatic). */
 EMVS_API int emvs_context_set_slab(emvs_context* ctx, uint32_t planes_per_slab);
+/* Tuning of emvs_mapper_evaluate_dsi on an idle pipeline: the first `percent` % of the event list is uploaded and
+ * voted first while the rest is still crossing PCIe, then the rest is voted into the same DSI (votes add).  Lists
+ * shorter than `min_events` are built in one piece; percent = 0 disables.  Defaults: 25 %, 2^20 events
+ * ($EMVS_UPLOAD_SPLIT overrides the percentage at context creation). */
+EMVS_API int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t min_events);
 /* Number of kernels this library launched on the context so far (bench `gpu_launches`). */
 EMVS_API int emvs_context_launch_count(emvs_context* ctx, uint64_t* out);
 /* Per-launch device timing of the vote kernel (the dominant kernel; bench.py's roofline):
@@ -203,6 +208,14 @@ EMVS_API int emvs_pose_inverse(const emvs_pose* a, emvs_pose* out);
 EMVS_API int emvs_packetize(const emvs_event* events, size_t n_events,
                    const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w,
                    const emvs_camera* cam, const float virt[4], float z0,
+                   emvs_packet* out, size_t max_packets, size_t* n_packets);
+/* Resumable form for streaming callers: continues the same packet loop from event index *cursor and stops before
+ * the first packet that would reach past `event_limit` (events [0, event_limit) are known so far; the full list
+ * has n_events).  *cursor is advanced; successive calls with growing limits produce exactly the packets of one
+ * emvs_packetize call over the whole list. */
+EMVS_API int emvs_packetize_range(const emvs_event* events, size_t n_events,
+                   const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w,
+                   const emvs_camera* cam, const float virt[4], float z0, size_t* cursor, size_t event_limit,
                    emvs_packet* out, size_t max_packets, size_t* n_packets);
 
 /* ---- Grid3D ------------------------------------------------------------------------------ */

@@ -31,3 +31,14 @@ def test_host_cpp_mirror_example():
     assert r.returncode == 0 and "example_process1 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     vol = np.load("/tmp/emvs_example_dsi.npy")                     # what the reference's viewers read
     assert vol.shape == (64, 180, 240) and vol.dtype == np.float32 and vol.sum() > 1e4
+
+
+def test_host_cpp_process_2_and_5_example():
+    """process_2 / process_5 (Alg. 2 and its shuffled variant) through the C++ mirror: AM commutes across the two
+    fusion orders, the reference's id swap in the time-then-camera switch, process_5 == process_2 for one
+    sub-interval, error returns."""
+    exe = os.path.join(ROOT, "dvs_mcemvs_b200", "host", "example_process2")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(exe)], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "example_process2 ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

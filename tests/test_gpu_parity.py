@@ -80,6 +80,40 @@ def test_evaluate_dsi_whole_path(ctx, small_case, built_small, O):
     m.close()
 
 
+@pytest.mark.parametrize("percent", [10, 25, 50, 90])
+def test_evaluate_dsi_split_upload(ctx, small_case, built_small, percent):
+    """evaluateDSI on an idle pipeline votes the head of the list while the tail is uploaded, then accumulates the
+    tail: same per-plane counts (bit-exact) and the same DSI up to float order as the one-piece build / the oracle."""
+    _, oracle = built_small
+    tr = api.LinearTrajectory(small_case.trajs[0])
+    m = api.MapperEMVS(ctx, small_case.cams[0], small_case.shape)
+    try:
+        ctx.sync()
+        ctx.set_upload_split(percent, 4096)
+        n0 = ctx.launch_count()
+        assert m.evaluateDSI(small_case.events[0], tr, small_case.T_rv_w) is True
+        n_split = ctx.launch_count() - n0
+        assert np.array_equal(m.counts(), oracle[0][1])
+        np.testing.assert_allclose(m.dsi_.download(), oracle[0][0], rtol=DSI_RTOL, atol=DSI_ATOL)
+        ctx.sync()
+        ctx.set_upload_split(0)
+        n0 = ctx.launch_count()
+        assert m.evaluateDSI(small_case.events[0], tr, small_case.T_rv_w) is True
+        n_whole = ctx.launch_count() - n0
+        assert n_split == 2 * n_whole      # head build + tail build really ran as two passes
+        assert np.array_equal(m.counts(), oracle[0][1])
+        np.testing.assert_allclose(m.dsi_.download(), oracle[0][0], rtol=DSI_RTOL, atol=DSI_ATOL)
+        # a second evaluateDSI with the split on must RESET, not keep accumulating into the previous result
+        ctx.set_upload_split(percent, 4096)
+        ctx.sync()
+        assert m.evaluateDSI(small_case.events[0], tr, small_case.T_rv_w) is True
+        assert np.array_equal(m.counts(), oracle[0][1])
+        np.testing.assert_allclose(m.dsi_.download(), oracle[0][0], rtol=DSI_RTOL, atol=DSI_ATOL)
+    finally:
+        ctx.set_upload_split(25)
+        m.close()
+
+
 def test_mean_square(built_small, O):
     mappers, oracle = built_small
     for m, (dsi_o, _) in zip(mappers, oracle):

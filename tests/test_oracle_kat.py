@@ -235,3 +235,37 @@ def test_product_host_geometry_matches_oracle_bit_exact(O, small_case):
     capi.check(lib.emvs_virtual_camera(C.byref(cs), C.byref(sh), capi.ptr(virt)))
     assert virt.tobytes() == O.virtual_camera(200.0, 120.0, 90.0, 120, 60.0).tobytes()
     assert virt[0] == pytest.approx(0.5 * 120 / np.tan(np.deg2rad(30.0)), rel=1e-6)
+
+
+def test_packetize_range_equals_one_shot(O):
+    """emvs_packetize_range with growing event limits (the split upload of evaluateDSI) yields exactly the packets of
+    one pass over the whole list — also when a run of pose misses straddles a limit (no GPU needed)."""
+    lib = capi.load()
+    K = np.array([200, 200, 120, 90], np.float32)
+    tr = _traj([100.0, 101.0], [[0, 0, 0], [0.1, 0, 0]])
+    I = np.zeros((), capi.POSE_DTYPE); I["q"] = (1, 0, 0, 0)
+    cam = capi.Camera(240, 180, 200, 200, 120, 90)
+    # events before the trajectory, inside, a gap after its end, so that misses occur at the head and at the tail
+    ts = np.concatenate([np.linspace(99.5, 99.99, 700), np.linspace(100.0, 100.99, 9000), np.linspace(101.01, 101.5, 2500)])
+    ev = np.zeros(len(ts), O.EVENT_DTYPE)
+    ev["sec"], ev["nsec"] = synth._split_time(ts)
+    want = O.packetize(ev, tr, I, K, K.copy(), 1.0)
+    assert len(want) >= 8
+    for limits in ([len(ev)], [1024, len(ev)], [3000, 3001, 7777, len(ev)], [0, 500, 1023, 2048, 9700 + 512, len(ev)],
+                   list(range(0, len(ev), 1000)) + [len(ev)]):
+        cur = C.c_size_t(0)
+        got = []
+        for lim in limits:
+            out = np.zeros(len(ev) // 1024 + 1, capi.PACKET_DTYPE)
+            n = C.c_size_t(0)
+            capi.check(lib.emvs_packetize_range(capi.ptr(ev), len(ev), capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam),
+                                                capi.ptr(K), 1.0, C.byref(cur), lim, capi.ptr(out), len(out), C.byref(n)))
+            assert np.all(out["first_event"][:n.value] + 1024 <= lim)
+            got.append(out[:n.value].copy())
+        got = np.concatenate(got)
+        assert got.tobytes() == want.tobytes(), limits
+    cur = C.c_size_t(len(ev) + 1)   # cursor past the list is rejected
+    n = C.c_size_t(0)
+    out = np.zeros(4, capi.PACKET_DTYPE)
+    assert lib.emvs_packetize_range(capi.ptr(ev), len(ev), capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam), capi.ptr(K), 1.0,
+                                    C.byref(cur), len(ev), capi.ptr(out), 4, C.byref(n)) == capi.EMVS_ERR_INVALID
