@@ -1363,7 +1363,8 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
   if (ctx->split_percent && !exchange && n_events >= ctx->split_min_events && n_events >= 4 * (size_t)EMVS_PACKET_SIZE) {
     const cudaError_t q = cudaStreamQuery(ctx->stream);
     if (q == cudaSuccess) n_head = (n_events / 100 * ctx->split_percent) / EMVS_PACKET_SIZE * EMVS_PACKET_SIZE;
-    else if (q != cudaErrorNotReady) CUDA_TRY(q);
+    else if (q == cudaErrorNotReady) (void)cudaGetLastError();   // "busy" is an answer, not an error: do not leave it behind
+    else CUDA_TRY(q);
   }
   int rc;
   if (n_head >= EMVS_PACKET_SIZE) {
