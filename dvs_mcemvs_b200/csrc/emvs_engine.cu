@@ -309,7 +309,11 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   const uint32_t QW = ceil_div(dimX, 2), QH = ceil_div(dimY, 2);
   const uint32_t slab = choose_slab(ctx, dimX, dimY, dimZ);
   // plane-grouped scratch layout + k_vote_grouped<G> (EMVS_VOTE_GROUP=1 selects the plain one-plane-per-instruction kernel)
-  static const uint32_t group_env = [] { const char* e = getenv("EMVS_VOTE_GROUP"); const int g = e ? atoi(e) : 2; return (uint32_t)(g == 4 ? 4 : g == 1 ? 1 : 2); }();
+  static const uint32_t group_env = [] {
+    const char* e = getenv("EMVS_VOTE_GROUP");
+    const int g = e ? atoi(e) : 4;
+    return (uint32_t)((g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 4);
+  }();
   const uint32_t G = group_env;
   auto round_up_g = [&](uint32_t n) { return (n + G - 1) / G * G; };
   const size_t slab_bytes = (size_t)round_up_g(slab) * QW * QH * 4 * sizeof(float4);
@@ -360,15 +364,20 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       ctx->prof_used += 2;
       CUDA_TRY(cudaEventRecord(pe0, st));
     }
-    if (G == 2)
-      k_vote_grouped<2><<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
-                                                                         m->d_counts);
-    else if (G == 4)
-      k_vote_grouped<4><<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
-                                                                         m->d_counts);
-    else
-      k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b],
-                                                              m->d_counts);
+    const size_t smem_g = smem + EMVS_PACKET_SIZE * sizeof(float2);   // + the packet's warped events
+#define LAUNCH_VOTE_G(GG)                                                                                              \
+  k_vote_grouped<GG><<<(unsigned)n_packets, kVoteThreads, smem_g, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], \
+                                                                        m->d_counts)
+    switch (G) {
+      case 2: LAUNCH_VOTE_G(2); break;
+      case 4: LAUNCH_VOTE_G(4); break;
+      case 8: LAUNCH_VOTE_G(8); break;
+      case 16: LAUNCH_VOTE_G(16); break;
+      case 32: LAUNCH_VOTE_G(32); break;
+      default:
+        k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], m->d_counts);
+    }
+#undef LAUNCH_VOTE_G
     ctx->launches++;
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
     if (overlap) {

@@ -269,3 +269,40 @@ def test_packetize_range_equals_one_shot(O):
     out = np.zeros(4, capi.PACKET_DTYPE)
     assert lib.emvs_packetize_range(capi.ptr(ev), len(ev), capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam), capi.ptr(K), 1.0,
                                     C.byref(cur), len(ev), capi.ptr(out), 4, C.byref(n)) == capi.EMVS_ERR_INVALID
+
+
+def test_parallel_packetizer_equals_sequential_oracle(O):
+    """Long lists take the speculative multi-threaded path of the product's packet stage (packets at cur + 1024*j
+    computed by several threads, longest all-successful prefix kept).  It must reproduce the sequential loop bit for
+    bit, including the one-event slides at both ends of the trajectory (no GPU needed)."""
+    lib = capi.load()
+    K = np.array([200, 200, 120, 90], np.float32)
+    rng = np.random.default_rng(5)
+    t_ctrl = np.linspace(100.0, 101.0, 21)
+    pos = np.cumsum(rng.normal(0, 0.01, (21, 3)), axis=0)
+    tr = _traj(t_ctrl.tolist(), pos.tolist())
+    I = np.zeros((), capi.POSE_DTYPE); I["q"] = (1, 0, 0, 0)
+    cam = capi.Camera(240, 180, 200, 200, 120, 90)
+    n_in = 1024 * 1500 + 77
+    ts = np.concatenate([np.linspace(99.9, 99.999, 3000), np.sort(rng.uniform(100.0, 100.999, n_in)),
+                         np.linspace(101.001, 101.2, 2600)])
+    ev = np.zeros(len(ts), O.EVENT_DTYPE)
+    ev["sec"], ev["nsec"] = synth._split_time(ts)
+    want = O.packetize(ev, tr, I, K, K.copy(), 1.0)
+    assert len(want) > 1400 and want["first_event"][0] == 3000 - 512
+    for limits in ([len(ev)], [700_000, len(ev)], [1024 * 600, 1024 * 600 + 5, 1_400_000, len(ev) - 1, len(ev)]):
+        cur = C.c_size_t(0)
+        got = []
+        for lim in limits:
+            out = np.zeros(len(ev) // 1024 + 1, capi.PACKET_DTYPE)
+            n = C.c_size_t(0)
+            capi.check(lib.emvs_packetize_range(capi.ptr(ev), len(ev), capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam),
+                                                capi.ptr(K), 1.0, C.byref(cur), lim, capi.ptr(out), len(out), C.byref(n)))
+            got.append(out[:n.value].copy())
+        assert np.concatenate(got).tobytes() == want.tobytes(), limits
+    # output capacity smaller than the list: exactly max_packets packets, the same ones
+    out = np.zeros(1000, capi.PACKET_DTYPE)
+    n = C.c_size_t(0)
+    capi.check(lib.emvs_packetize(capi.ptr(ev), len(ev), capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam), capi.ptr(K), 1.0,
+                                  capi.ptr(out), 1000, C.byref(n)))
+    assert n.value == 1000 and out.tobytes() == want[:1000].tobytes()
