@@ -142,6 +142,13 @@ class Context:
         """evaluateDSI on an idle pipeline votes the first `percent` % of the events while the rest is uploaded."""
         check(_lib().emvs_context_set_upload_split(self._h, int(percent), int(min_events)))
 
+    def prefetch_events(self, events):
+        """Start uploading the event list of a LATER evaluateDSI / build call (same array object) now, under the
+        current work.  `events` must already be contiguous EVENT_DTYPE (ideally pinned) and stay unchanged."""
+        if events.dtype != EVENT_DTYPE or not events.flags["C_CONTIGUOUS"]:
+            raise ValueError("prefetch_events needs a contiguous EVENT_DTYPE array (the later call must see the same buffer)")
+        check(_lib().emvs_context_prefetch_events(self._h, ptr(events), events.shape[0]))
+
     def launch_count(self):
         n = C.c_uint64(0)
         check(_lib().emvs_context_launch_count(self._h, C.byref(n)))

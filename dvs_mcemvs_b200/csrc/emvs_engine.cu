@@ -72,15 +72,25 @@ struct emvs_context {
   bool merge_pending[2] = {false, false};
   bool overlap = true;
   // grow-only device staging
-  void* d_events = nullptr;  size_t events_cap = 0;
+  // two event staging buffers: the list of the next build (or a prefetched list) is uploaded into one while the
+  // event stage of the current build may still be reading the other
+  void* d_events[2] = {nullptr, nullptr};  size_t events_cap[2] = {0, 0};
+  unsigned upload_next = 0;            // staging buffer the next upload goes to
+  int cur_events = 0;                  // staging buffer the current / last host-buffer build reads
+  struct {                             // emvs_context_prefetch_events: a list already on its way to d_events[buf]
+    const emvs_event* host = nullptr;
+    size_t n = 0;
+    int buf = 0;
+    bool valid = false;
+  } prefetch;
   void* d_packets[2] = {nullptr, nullptr}; size_t packets_cap[2] = {0, 0};  // alternate per build (see build_from_host)
   unsigned build_parity = 0;
   // host->device staging runs on its own stream so that the upload of the next camera's events
   // overlaps the vote kernels of the previous one
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied = nullptr;     // inputs of the current build are in HBM
-  cudaEvent_t ev_consumed = nullptr;   // k_warp_events of the last build has read d_events
-  bool consumed_recorded = false;
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // k_warp_events of the last build on d_events[i] has read it
+  bool consumed_recorded[2] = {false, false};
   bool mark_consumed = false;          // build_on_device records ev_consumed after the event stage
   float2* d_xy0 = nullptr;   size_t xy0_cap = 0;
   void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
@@ -176,25 +186,45 @@ int grow(void** p, size_t* cap, size_t need)
 
 inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-// Planes voted per pass over the event list.  The quad scratch of a slab (4 copies) must stay
-// L2-resident together with the streaming event reads.  Measured on B200 (126 MB L2) at
-// 640x480: 16 planes (79 MB) is the fastest, 32 planes (157 MB) falls off the L2 cliff
-// (profiles/r1_slab_sweep.md).  With the double-buffered scratch (merge of slab s overlapped with
-// the votes of slab s+1) 2 x 12 planes (118 MB) measured fastest: 59 MiB per buffer.
-uint32_t choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ)
+// Planes voted per pass over the event list (the slab) and planes whose quads are interleaved in the scratch (the
+// plane group G of k_vote_grouped).  Measured on B200 (126 MB L2) at 640x480, profiles/r1_vote_group.md:
+//   * G = 8 with the events staged in shared memory and the grouped merge is the fastest (1235 Mevents/s against
+//     1097 at G = 4, 811 at G = 2, 739 ungrouped); G = 16 is no better;
+//   * two scratch buffers of 16 planes (79 MB each; slab s is voted while slab s-1 is merged and re-zeroed) beat
+//     2 x 8 (1200) and one buffer of 16 without overlap (1175), although together they exceed the L2.
+// The slab is a multiple of G (idle lanes otherwise); DSIs whose planes are so large that fewer than 8 fit the
+// budget get a smaller group.
+struct SlabPlan {
+  uint32_t slab, group;
+};
+
+SlabPlan choose_slab(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ)
 {
+  static const uint32_t group_env = [] {
+    const char* e = getenv("EMVS_VOTE_GROUP");
+    const int g = e ? atoi(e) : 0;
+    return (uint32_t)((g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 0);
+  }();
   uint32_t s = ctx->slab_override;
   if (!s) {
     if (const char* env = getenv("EMVS_SLAB")) s = (uint32_t)atoi(env);
   }
+  const bool fixed = s != 0;
   if (!s) {
     const size_t plane_bytes = (size_t)ceil_div(dimX, 2) * ceil_div(dimY, 2) * 64;
-    const size_t budget = ctx->overlap ? ((size_t)59 << 20) : ((size_t)80 << 20);   // per buffer; two buffers when overlapped
+    const size_t budget = (size_t)80 << 20;   // per buffer; two buffers when overlapped
     s = (uint32_t)std::max<size_t>(1, budget / std::max<size_t>(plane_bytes, 1));
   }
   s = std::min(s, dimZ);
   s = std::min<uint32_t>(s, 1024);
-  return std::max<uint32_t>(s, 1);
+  s = std::max<uint32_t>(s, 1);
+  uint32_t g = group_env;
+  if (!g) {
+    g = 8;
+    while (g > 1 && g > s) g >>= 1;
+  }
+  if (!fixed && s > g) s = s / g * g;
+  return SlabPlan{s, g};
 }
 
 int ensure_quad(emvs_context* ctx, int b, size_t bytes)
@@ -282,7 +312,7 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   if (n_packets == 0) {
     if (!accumulate) CUDA_TRY(cudaMemsetAsync(g->d, 0, g->n_cells * sizeof(float), st));
     if (reduce) {  // this rank has no packets but must issue the SAME sequence of collectives as the others
-      const uint32_t zslab = choose_slab(ctx, g->dimX, g->dimY, g->dimZ);
+      const uint32_t zslab = choose_slab(ctx, g->dimX, g->dimY, g->dimZ).slab;
       const size_t plane = (size_t)g->dimX * g->dimY;
       for (uint32_t k0 = 0; k0 < g->dimZ; k0 += zslab) {
         const uint32_t nk = std::min(zslab, g->dimZ - k0);
@@ -291,7 +321,7 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, g->dimZ, st)) return EMVS_ERR_NCCL;
     }
     if (peer) {    // an all-zero partial DSI: announce and reduce the same slabs as the ranks that do vote
-      const uint32_t zslab = choose_slab(ctx, g->dimX, g->dimY, g->dimZ);
+      const uint32_t zslab = choose_slab(ctx, g->dimX, g->dimY, g->dimZ).slab;
       for (uint32_t k0 = 0; k0 < g->dimZ; k0 += zslab) {
         const int rc = peer_reduce_slab(ctx, ex, peer_cam, k0 / zslab, k0, std::min(zslab, g->dimZ - k0), st);
         if (rc) return rc;   // (emvs_exchange_fuse_collapse waits for the communication stream)
@@ -307,14 +337,10 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
   }
   const uint32_t dimX = g->dimX, dimY = g->dimY, dimZ = g->dimZ;
   const uint32_t QW = ceil_div(dimX, 2), QH = ceil_div(dimY, 2);
-  const uint32_t slab = choose_slab(ctx, dimX, dimY, dimZ);
+  const SlabPlan plan = choose_slab(ctx, dimX, dimY, dimZ);
+  const uint32_t slab = plan.slab;
   // plane-grouped scratch layout + k_vote_grouped<G> (EMVS_VOTE_GROUP=1 selects the plain one-plane-per-instruction kernel)
-  static const uint32_t group_env = [] {
-    const char* e = getenv("EMVS_VOTE_GROUP");
-    const int g = e ? atoi(e) : 4;
-    return (uint32_t)((g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 4);
-  }();
-  const uint32_t G = group_env;
+  const uint32_t G = plan.group;
   auto round_up_g = [&](uint32_t n) { return (n + G - 1) / G * G; };
   const size_t slab_bytes = (size_t)round_up_g(slab) * QW * QH * 4 * sizeof(float4);
   const bool overlap = ctx->overlap;
@@ -329,8 +355,8 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
                                           (unsigned long long)n_voted);
     ctx->launches++;
     if (ctx->mark_consumed) {
-      CUDA_TRY(cudaEventRecord(ctx->ev_consumed, st));
-      ctx->consumed_recorded = true;
+      CUDA_TRY(cudaEventRecord(ctx->ev_consumed[ctx->cur_events], st));
+      ctx->consumed_recorded[ctx->cur_events] = true;
     }
   }
 
@@ -384,9 +410,24 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       CUDA_TRY(cudaEventRecord(ctx->ev_vote[b], st));
       CUDA_TRY(cudaStreamWaitEvent(ms, ctx->ev_vote[b], 0));
     }
-    dim3 mb(32, 8, 1), mg(ceil_div(QW, 32), ceil_div(QH, 8), nk);
-    k_merge_quads<<<mg, mb, 0, ms>>>(ctx->quad[b], g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
-                                     accumulate ? 1 : 0, (int)G);
+    static const bool merge_grouped = [] { const char* e = getenv("EMVS_MERGE_GROUPED"); return e ? atoi(e) != 0 : true; }();
+    if (G > 1 && merge_grouped) {
+      const dim3 mg(ceil_div(QW, 256 / G), QH, ceil_div(nk, G));
+      float* dst = g->d + (size_t)k0 * dimX * dimY;
+#define LAUNCH_MERGE_G(GG) k_merge_quads_grouped<GG><<<mg, 256, 0, ms>>>(ctx->quad[b], dst, dimX, dimY, QW, QH, nk, accumulate ? 1 : 0)
+      switch (G) {
+        case 2: LAUNCH_MERGE_G(2); break;
+        case 4: LAUNCH_MERGE_G(4); break;
+        case 8: LAUNCH_MERGE_G(8); break;
+        case 16: LAUNCH_MERGE_G(16); break;
+        default: LAUNCH_MERGE_G(32); break;
+      }
+#undef LAUNCH_MERGE_G
+    } else {
+      dim3 mb(32, 8, 1), mg(ceil_div(QW, 32), ceil_div(QH, 8), nk);
+      k_merge_quads<<<mg, mb, 0, ms>>>(ctx->quad[b], g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
+                                       accumulate ? 1 : 0, (int)G);
+    }
     ctx->launches++;
     CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, (size_t)round_up_g(nk) * QW * QH * 4 * sizeof(float4), ms));
     if (overlap) {
@@ -571,7 +612,7 @@ int emvs_context_create(int device, emvs_context** out)
   if (const char* env = getenv("EMVS_OVERLAP")) ctx->overlap = atoi(env) != 0;
   if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed, cudaEventDisableTiming);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_partial, sizeof(double) * 1025);
   if (e != cudaSuccess) {
     set_error("context_create: %s", cudaGetErrorString(e));
@@ -608,14 +649,16 @@ static void context_release(emvs_context* ctx)
   }
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-  cudaFree(ctx->d_events);
+  cudaFree(ctx->d_events[0]);
+  cudaFree(ctx->d_events[1]);
   cudaFree(ctx->d_packets[0]);
   cudaFree(ctx->d_packets[1]);
   for (cudaEvent_t e : ctx->slab_events) cudaEventDestroy(e);
   if (ctx->ev_comm_done) cudaEventDestroy(ctx->ev_comm_done);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
-  if (ctx->ev_consumed) cudaEventDestroy(ctx->ev_consumed);
+  for (int b = 0; b < 2; ++b)
+    if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_xy0);
   cudaFree(ctx->d_out);
@@ -648,6 +691,26 @@ int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t 
   REQUIRE(percent <= 90, EMVS_ERR_INVALID, "set_upload_split: percent must be 0..90");
   ctx->split_percent = percent;
   ctx->split_min_events = (size_t)min_events;
+  return EMVS_OK;
+}
+
+static int stage_events(emvs_context* ctx, size_t n_events);
+
+int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, size_t n_events)
+{
+  REQUIRE(ctx && events && n_events, EMVS_ERR_INVALID, "prefetch_events: NULL argument or empty list");
+  DeviceGuard guard(ctx->device);
+  ctx->prefetch.valid = false;          // an earlier, unconsumed prefetch is dropped: its buffer is free again
+  const int keep = ctx->cur_events;     // stage_events moves cur_events; the current build keeps its own buffer
+  const int rc = stage_events(ctx, n_events);
+  const int buf = ctx->cur_events;
+  ctx->cur_events = keep;
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_events[buf], events, n_events * sizeof(emvs_event), cudaMemcpyHostToDevice, ctx->copy_stream));
+  ctx->prefetch.host = events;
+  ctx->prefetch.n = n_events;
+  ctx->prefetch.buf = buf;
+  ctx->prefetch.valid = true;
   return EMVS_OK;
 }
 
@@ -1257,19 +1320,41 @@ static int check_packets(const emvs_packet* pk, size_t n_packets, size_t n_event
 }
 
 // Host-buffer build.  Staging protocol (one context = one in-order pipeline):
-//   copy_stream:  wait(ev_consumed of the previous build) -> H2D events, packets -> record ev_copied
+//   copy_stream:  wait(ev_consumed of the staging buffer's previous build) -> H2D events, packets -> record ev_copied
 //   stream:       wait(ev_copied) -> k_warp_events -> record ev_consumed -> slab loop
 //   host:         waits for ev_copied only, so the caller may reuse its buffers and issue the next
 //                 camera's build, whose upload then overlaps this build's vote kernels.
 // d_events is read by k_warp_events only; d_packets is read by every vote launch, hence two
 // alternating packet buffers: build N+2 can only upload after k_warp_events of build N+1 ran,
 // which is stream-ordered behind the last vote of build N.
+// Picks the staging buffer of the next upload (never the one that holds a pending prefetch), sizes it for the
+// list and orders the copy stream behind the last event stage that read it.  It becomes the current buffer.
+static int stage_events(emvs_context* ctx, size_t n_events)
+{
+  int u = (int)(ctx->upload_next & 1u);
+  if (ctx->prefetch.valid && ctx->prefetch.buf == u) u ^= 1;
+  ctx->upload_next = (unsigned)u + 1u;
+  const int rc = grow(&ctx->d_events[u], &ctx->events_cap[u], n_events * sizeof(emvs_event));
+  if (rc) return rc;
+  if (ctx->consumed_recorded[u]) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[u], 0));
+  ctx->cur_events = u;
+  return EMVS_OK;
+}
+
+// A list announced with emvs_context_prefetch_events is already in (or on its way to) a staging buffer.
+static bool take_prefetch(emvs_context* ctx, const emvs_event* events, size_t n_events)
+{
+  if (!ctx->prefetch.valid || ctx->prefetch.host != events || ctx->prefetch.n != n_events) return false;
+  ctx->prefetch.valid = false;
+  ctx->cur_events = ctx->prefetch.buf;
+  return true;
+}
+
 static int upload_events(emvs_context* ctx, const emvs_event* events, size_t n_events, size_t lo, size_t hi)
 {
-  int rc = grow(&ctx->d_events, &ctx->events_cap, n_events * sizeof(emvs_event));
+  const int rc = stage_events(ctx, n_events);
   if (rc) return rc;
-  if (ctx->consumed_recorded) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed, 0));
-  CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + lo, events + lo, (hi - lo) * sizeof(emvs_event),
+  CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events[ctx->cur_events] + lo, events + lo, (hi - lo) * sizeof(emvs_event),
                            cudaMemcpyHostToDevice, ctx->copy_stream));
   return EMVS_OK;
 }
@@ -1283,7 +1368,7 @@ static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_ev
   emvs_context* ctx = m->ctx;
   const unsigned par = ctx->build_parity++ & 1u;
   if (n_packets) {
-    if (!events_uploaded) {
+    if (!events_uploaded && !take_prefetch(ctx, events, n_events)) {
       size_t lo = n_events, last = 0;   // only the span of events that packets reference has to travel
       for (size_t j = 0; j < n_packets; ++j) {
         lo = std::min<size_t>(lo, packets[j].first_event);
@@ -1302,10 +1387,10 @@ static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_ev
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
   }
   if (tail_hi > tail_lo)
-    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + tail_lo, events + tail_lo, (tail_hi - tail_lo) * sizeof(emvs_event),
+    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events[ctx->cur_events] + tail_lo, events + tail_lo, (tail_hi - tail_lo) * sizeof(emvs_event),
                              cudaMemcpyHostToDevice, ctx->copy_stream));
   ctx->mark_consumed = true;
-  const int rc = build_on_device(m, (const emvs_event*)ctx->d_events, n_events, (const emvs_packet*)ctx->d_packets[par],
+  const int rc = build_on_device(m, (const emvs_event*)ctx->d_events[ctx->cur_events], n_events, (const emvs_packet*)ctx->d_packets[par],
                                  n_packets, flags);
   ctx->mark_consumed = false;
   if (rc) return rc;
@@ -1367,6 +1452,16 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
   // (voting is a sum over events, so head + tail == whole list up to float summation order; the per-plane
   // counters add exactly).  When the stream is busy (the previous camera is still voting) the whole upload is
   // already hidden and the list is built in one piece.  The slab-wise exchanges need final slabs: no split.
+  if (take_prefetch(ctx, events, n_events)) {
+    // the list was announced earlier (emvs_context_prefetch_events): nothing to upload, the packet stage is all
+    // that stands between the call and the first vote
+    const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
+                                       ctx->h_packets, max_pk);
+    const int rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, flags, true);
+    if (rc) return rc;
+    if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    return EMVS_OK;
+  }
   const bool exchange = (flags & (EMVS_BUILD_ALLREDUCE | EMVS_BUILD_PEER_REDUCE)) != 0;
   size_t n_head = 0;
   if (ctx->split_percent && !exchange && n_events >= ctx->split_min_events && n_events >= 4 * (size_t)EMVS_PACKET_SIZE) {
@@ -1396,7 +1491,7 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
       return EMVS_OK;
     }
     // no packet in the head (every pose lookup missed): upload the rest and build in one piece
-    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events + n_head, events + n_head, (n_events - n_head) * sizeof(emvs_event),
+    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events[ctx->cur_events] + n_head, events + n_head, (n_events - n_head) * sizeof(emvs_event),
                              cudaMemcpyHostToDevice, ctx->copy_stream));
     const size_t n_pk = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
                                              n_events, ctx->h_packets, max_pk);

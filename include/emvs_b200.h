@@ -159,6 +159,12 @@ EMVS_API int emvs_context_set_slab(emvs_context* ctx, uint32_t planes_per_slab);
  * shorter than `min_events` are built in one piece; percent = 0 disables.  Defaults: 25 %, 2^20 events
  * ($EMVS_UPLOAD_SPLIT overrides the percentage at context creation). */
 EMVS_API int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t min_events);
+/* Streaming callers (consecutive windows, main.cpp:177-431 full_seq loop): announce the event list of a LATER
+ * emvs_mapper_evaluate_dsi / emvs_mapper_build call.  Its host->device copy starts now, on the copy stream, under
+ * whatever the context is computing; the later call recognises the list by (pointer, n_events) and skips its own
+ * upload.  Returns immediately.  The list must stay valid and unchanged until that call has returned; one
+ * prefetch can be pending per context (a new one replaces it); other lists may be built in between. */
+EMVS_API int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, size_t n_events);
 /* Number of kernels this library launched on the context so far (bench `gpu_launches`). */
 EMVS_API int emvs_context_launch_count(emvs_context* ctx, uint64_t* out);
 /* Per-launch device timing of the vote kernel (the dominant kernel; bench.py's roofline):

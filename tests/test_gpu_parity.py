@@ -114,6 +114,55 @@ def test_evaluate_dsi_split_upload(ctx, small_case, built_small, percent):
         m.close()
 
 
+def test_prefetch_events(ctx, small_case, built_small):
+    """A list announced with prefetch_events is uploaded ahead of its evaluateDSI, other lists may be built in
+    between, and a replaced / unmatched prefetch falls back to the ordinary upload."""
+    import time
+    _, oracle = built_small
+    trs = [api.LinearTrajectory(t) for t in small_case.trajs]
+    ms = [api.MapperEMVS(ctx, c, small_case.shape) for c in small_case.cams[:2]]
+    pinned = []
+    for i in range(2):
+        buf = api.pinned_empty(small_case.events[i].shape, small_case.events[i].dtype)
+        buf[...] = small_case.events[i]
+        pinned.append(buf)
+
+    def check(i):
+        assert np.array_equal(ms[i].counts(), oracle[i][1])
+        np.testing.assert_allclose(ms[i].dsi_.download(), oracle[i][0], rtol=DSI_RTOL, atol=DSI_ATOL)
+    try:
+        ctx.prefetch_events(pinned[0])
+        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)      # an unrelated list in between
+        # white box: once the prefetch copy has landed, scribble over the pixel coordinates on the host (timestamps,
+        # which the host packet stage reads, stay).  Only the prefetched device copy still holds the real events.
+        time.sleep(0.2)
+        saved = pinned[0]["x"].copy()
+        pinned[0]["x"] = 0
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+        pinned[0]["x"] = saved
+        check(0); check(1)
+        # a second prefetch replaces the first; the replaced list is then uploaded the ordinary way
+        ctx.prefetch_events(pinned[0])
+        ctx.prefetch_events(pinned[1])
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)
+        check(0); check(1)
+        # steady state of a streaming caller: prefetch the next window's first list before collecting this window's maps
+        for _ in range(3):
+            assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+            assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)
+            ctx.prefetch_events(pinned[0])
+            conf, idx, depth = api.fuse_collapse([m.dsi_ for m in ms], 2, ms[0].raw_depths_vec_)
+        check(0); check(1)
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)      # consume the last prefetch
+        check(0)
+        with pytest.raises(ValueError):
+            ctx.prefetch_events(small_case.events[0][::2])
+    finally:
+        for m in ms:
+            m.close()
+
+
 def test_mean_square(built_small, O):
     mappers, oracle = built_small
     for m, (dsi_o, _) in zip(mappers, oracle):
