@@ -365,7 +365,7 @@ def run_b200(args):
             if not args.no_prefetch:
                 # streaming caller: the NEXT step's first event list starts crossing PCIe now, under this step's
                 # votes (every step still uploads every list once, inside the timed region)
-                ctx.prefetch_events(h_events[0])
+                mappers[0].prefetch(h_events[0], ltrajs[0], T_rv_w)
             if peer is not None:
                 peer.fuse_collapse(method, d_tab)
                 return peer.download()
@@ -410,8 +410,9 @@ def run_b200(args):
                "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": e2e_s * 1e3,
                "timer": "host wall clock around the blocking public calls (each call syncs its stream)",
                "prefetch": ("off" if args.no_prefetch else
-                            "the next step's first event list is announced with emvs_context_prefetch_events after the "
-                            "last evaluateDSI of a step; every list is uploaded once per step inside the timed region")}
+                            "the next step's first evaluateDSI is announced with emvs_mapper_prefetch_dsi after the last "
+                            "evaluateDSI of a step (its upload and host packet stage run under the current votes); every "
+                            "list is uploaded and packetised once per step inside the timed region")}
 
     if rank == 0:
         peak, peak_src = load_peaks()

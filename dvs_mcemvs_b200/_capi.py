@@ -65,6 +65,8 @@ _PROTOTYPES = {
     "emvs_context_set_slab": (C.c_int, [_vp, C.c_uint32]),
     "emvs_context_set_upload_split": (C.c_int, [_vp, C.c_uint32, C.c_uint64]),
     "emvs_context_prefetch_events": (C.c_int, [_vp, _vp, _sz]),
+    "emvs_mapper_prefetch_dsi": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "emvs_selftest_division": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "emvs_context_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "emvs_context_profile_vote": (C.c_int, [_vp, C.c_int]),
     "emvs_context_vote_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -149,6 +149,12 @@ class Context:
             raise ValueError("prefetch_events needs a contiguous EVENT_DTYPE array (the later call must see the same buffer)")
         check(_lib().emvs_context_prefetch_events(self._h, ptr(events), events.shape[0]))
 
+    def selftest_division(self, n_pairs=1 << 28, seed=1):
+        """Mismatches between the vote kernel's prepared division and __fdiv_rn over ~n_pairs operand pairs."""
+        bad = C.c_uint64(0)
+        check(_lib().emvs_selftest_division(self._h, int(n_pairs), int(seed), C.byref(bad)))
+        return bad.value
+
     def launch_count(self):
         n = C.c_uint64(0)
         check(_lib().emvs_context_launch_count(self._h, C.byref(n)))
@@ -488,6 +494,16 @@ class MapperEMVS:
                                           ptr(self.virtual_cam_), float(self.raw_depths_vec_[0]), C.byref(cur),
                                           int(event_limit), ptr(out), out.shape[0], C.byref(n_pk)))
         return out[:n_pk.value], cur.value
+
+    def prefetch(self, events, trajectory, T_rv_w):
+        """Streaming callers: start the upload AND the host packet stage of a LATER evaluateDSI(events, trajectory,
+        T_rv_w) on this mapper now, under the current device work; that call then only launches kernels.  `events`
+        must be the same contiguous EVENT_DTYPE array object (ideally pinned), `trajectory` the same object."""
+        if events.dtype != EVENT_DTYPE or not events.flags["C_CONTIGUOUS"]:
+            raise ValueError("prefetch needs a contiguous EVENT_DTYPE array (the later call must see the same buffer)")
+        check(_lib().emvs_mapper_prefetch_dsi(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
+                                              trajectory.poses.shape[0],
+                                              ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE))))
 
     def evaluateDSI(self, events, trajectory, T_rv_w, allreduce=False, peer_reduce=False):
         """bool evaluateDSI(events, trajectory, T_rv_w) — mapper_emvs_stereo.cpp:67-148.

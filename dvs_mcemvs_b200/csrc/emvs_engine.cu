@@ -82,9 +82,22 @@ struct emvs_context {
     size_t n = 0;
     int buf = 0;
     bool valid = false;
+    // emvs_mapper_prefetch_dsi: its packet stage has run too and the packets are on their way to d_packets[par]
+    bool has_packets = false;
+    size_t n_pk = 0;
+    unsigned par = 0;
+    const struct emvs_mapper* mapper = nullptr;
+    const emvs_stamped_pose* traj = nullptr;
+    size_t n_poses = 0;
+    emvs_pose T_rv_w{};
   } prefetch;
+  emvs_packet* h_packets_pf = nullptr; size_t h_packets_pf_cap = 0;   // pinned packets of the pending prefetch
+  cudaEvent_t ev_prefetched = nullptr;   // the prefetch's copies (events, packets) have landed
+  bool prefetched_recorded = false;
+  cudaEvent_t ev_pk_free[2] = {nullptr, nullptr};   // the last build reading d_packets[i] has finished voting
+  bool pk_free_recorded[2] = {false, false};
+  unsigned cur_packets = 0;            // d_packets buffer of the current host-buffer build
   void* d_packets[2] = {nullptr, nullptr}; size_t packets_cap[2] = {0, 0};  // alternate per build (see build_from_host)
-  unsigned build_parity = 0;
   // host->device staging runs on its own stream so that the upload of the next camera's events
   // overlaps the vote kernels of the previous one
   cudaStream_t copy_stream = nullptr;
@@ -390,10 +403,16 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       ctx->prof_used += 2;
       CUDA_TRY(cudaEventRecord(pe0, st));
     }
-    const size_t smem_g = smem + EMVS_PACKET_SIZE * sizeof(float2);   // + the packet's warped events
-#define LAUNCH_VOTE_G(GG)                                                                                              \
-  k_vote_grouped<GG><<<(unsigned)n_packets, kVoteThreads, smem_g, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], \
-                                                                        m->d_counts)
+    const size_t smem_g = smem + (EMVS_PACKET_SIZE + nk) * sizeof(float2);   // + the packet's warped events + prepared reciprocals
+    static const bool fastdiv = [] { const char* e = getenv("EMVS_VOTE_FASTDIV"); return e ? atoi(e) != 0 : false; }();
+#define LAUNCH_VOTE_GF(GG, FF)                                                                                         \
+  k_vote_grouped<GG, FF><<<(unsigned)n_packets, kVoteThreads, smem_g, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], \
+                                                                            m->d_counts)
+#define LAUNCH_VOTE_G(GG)                  \
+  do {                                     \
+    if (fastdiv) LAUNCH_VOTE_GF(GG, true); \
+    else LAUNCH_VOTE_GF(GG, false);        \
+  } while (0)
     switch (G) {
       case 2: LAUNCH_VOTE_G(2); break;
       case 4: LAUNCH_VOTE_G(4); break;
@@ -404,6 +423,7 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
         k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], m->d_counts);
     }
 #undef LAUNCH_VOTE_G
+#undef LAUNCH_VOTE_GF
     ctx->launches++;
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
     if (overlap) {
@@ -468,6 +488,10 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
     if (ncclAllReduceU64_checked(nccl, ctx, m->d_counts, dimZ, ctx->comm_stream)) return EMVS_ERR_NCCL;
     CUDA_TRY(cudaEventRecord(ctx->ev_comm_done, ctx->comm_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_comm_done, 0));
+  }
+  if (ctx->mark_consumed) {   // host-buffer build: its packet buffer may be overwritten once these votes are done
+    CUDA_TRY(cudaEventRecord(ctx->ev_pk_free[ctx->cur_packets], st));
+    ctx->pk_free_recorded[ctx->cur_packets] = true;
   }
   CUDA_TRY(cudaGetLastError());
   return EMVS_OK;
@@ -613,6 +637,8 @@ int emvs_context_create(int device, emvs_context** out)
   if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_pk_free[b], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_prefetched, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_partial, sizeof(double) * 1025);
   if (e != cudaSuccess) {
     set_error("context_create: %s", cudaGetErrorString(e));
@@ -665,6 +691,10 @@ static void context_release(emvs_context* ctx)
   cudaFree(ctx->d_fc_part);
   cudaFree(ctx->d_partial);
   if (ctx->h_packets) cudaFreeHost(ctx->h_packets);
+  if (ctx->h_packets_pf) cudaFreeHost(ctx->h_packets_pf);
+  if (ctx->ev_prefetched) cudaEventDestroy(ctx->ev_prefetched);
+  for (int b = 0; b < 2; ++b)
+    if (ctx->ev_pk_free[b]) cudaEventDestroy(ctx->ev_pk_free[b]);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -695,6 +725,7 @@ int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t 
 }
 
 static int stage_events(emvs_context* ctx, size_t n_events);
+static int stage_packets(emvs_context* ctx, size_t n_packets_cap, unsigned* par_out);
 
 int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, size_t n_events)
 {
@@ -711,6 +742,65 @@ int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, si
   ctx->prefetch.n = n_events;
   ctx->prefetch.buf = buf;
   ctx->prefetch.valid = true;
+  ctx->prefetch.has_packets = false;
+  return EMVS_OK;
+}
+
+int emvs_selftest_division(emvs_context* ctx, uint64_t n_pairs, uint32_t seed, uint64_t* mismatches)
+{
+  REQUIRE(ctx && mismatches, EMVS_ERR_INVALID, "selftest_division: NULL argument");
+  DeviceGuard guard(ctx->device);
+  unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(ctx->d_partial);   // scratch of the context
+  CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->stream));
+  const unsigned blocks = (unsigned)ctx->sm_count * 8u, threads = 256u;
+  const uint64_t per_thread = std::max<uint64_t>(1, n_pairs / ((uint64_t)blocks * threads));
+  REQUIRE(per_thread <= 0x3fffffffull, EMVS_ERR_INVALID, "selftest_division: n_pairs too large");
+  k_selftest_division<<<blocks, threads, 0, ctx->stream>>>((uint32_t)per_thread, seed, d_bad);
+  ctx->launches++;
+  unsigned long long bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *mismatches = bad;
+  return EMVS_OK;
+}
+
+int emvs_mapper_prefetch_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_stamped_pose* traj,
+                             size_t n_poses, const emvs_pose* T_rv_w)
+{
+  REQUIRE(m && events && traj && T_rv_w, EMVS_ERR_INVALID, "prefetch_dsi: NULL argument");
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  if (n_events < EMVS_PACKET_SIZE) return EMVS_OK;   // the later evaluateDSI returns false without touching the device
+  emvs_context* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  // the pinned packet buffer of an earlier prefetch may still be in flight
+  if (ctx->prefetched_recorded) CUDA_TRY(cudaEventSynchronize(ctx->ev_prefetched));
+  int rc = emvs_context_prefetch_events(ctx, events, n_events);
+  if (rc) return rc;
+  const size_t max_pk = n_events / EMVS_PACKET_SIZE + 1;
+  if (max_pk > ctx->h_packets_pf_cap) {
+    if (ctx->h_packets_pf) CUDA_TRY(cudaFreeHost(ctx->h_packets_pf));
+    ctx->h_packets_pf = nullptr;
+    ctx->h_packets_pf_cap = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&ctx->h_packets_pf, max_pk * sizeof(emvs_packet), cudaHostAllocDefault));
+    ctx->h_packets_pf_cap = max_pk;
+  }
+  const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
+                                     ctx->h_packets_pf, max_pk);
+  unsigned par = 0;
+  rc = stage_packets(ctx, max_pk, &par);
+  if (rc) return rc;
+  if (n_pk)
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], ctx->h_packets_pf, n_pk * sizeof(emvs_packet), cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+  CUDA_TRY(cudaEventRecord(ctx->ev_prefetched, ctx->copy_stream));
+  ctx->prefetched_recorded = true;
+  ctx->prefetch.has_packets = true;
+  ctx->prefetch.n_pk = n_pk;
+  ctx->prefetch.par = par;
+  ctx->prefetch.mapper = m;
+  ctx->prefetch.traj = traj;
+  ctx->prefetch.n_poses = n_poses;
+  ctx->prefetch.T_rv_w = *T_rv_w;
   return EMVS_OK;
 }
 
@@ -1346,8 +1436,22 @@ static bool take_prefetch(emvs_context* ctx, const emvs_event* events, size_t n_
 {
   if (!ctx->prefetch.valid || ctx->prefetch.host != events || ctx->prefetch.n != n_events) return false;
   ctx->prefetch.valid = false;
+  ctx->prefetch.has_packets = false;
   ctx->cur_events = ctx->prefetch.buf;
   return true;
+}
+
+// Packet buffer of the next host-buffer build: alternates, never the one a pending prefetch has filled, and the
+// copy stream is ordered behind the votes of the last build that read it.
+static int stage_packets(emvs_context* ctx, size_t n_packets_cap, unsigned* par_out)
+{
+  unsigned par = ctx->cur_packets ^ 1u;   // not the one the latest build is voting from
+  if (ctx->prefetch.valid && ctx->prefetch.has_packets && ctx->prefetch.par == par) par ^= 1u;
+  const int rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par], n_packets_cap * sizeof(emvs_packet));
+  if (rc) return rc;
+  if (ctx->pk_free_recorded[par]) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pk_free[par], 0));
+  *par_out = par;
+  return EMVS_OK;
 }
 
 static int upload_events(emvs_context* ctx, const emvs_event* events, size_t n_events, size_t lo, size_t hi)
@@ -1366,7 +1470,13 @@ static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_ev
                            size_t n_packets, int flags, bool events_uploaded, size_t tail_lo = 0, size_t tail_hi = 0)
 {
   emvs_context* ctx = m->ctx;
-  const unsigned par = ctx->build_parity++ & 1u;
+  unsigned par = 0;
+  {
+    // sized for the whole list so that head / tail / whole-list builds alternating over the two buffers never regrow them
+    const int rc = stage_packets(ctx, std::max(n_packets, n_events / EMVS_PACKET_SIZE + 1), &par);
+    if (rc) return rc;
+  }
+  ctx->cur_packets = par;
   if (n_packets) {
     if (!events_uploaded && !take_prefetch(ctx, events, n_events)) {
       size_t lo = n_events, last = 0;   // only the span of events that packets reference has to travel
@@ -1377,10 +1487,6 @@ static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_ev
       const int rc = upload_events(ctx, events, n_events, lo, last);
       if (rc) return rc;
     }
-    // sized for the whole list so that head / tail / whole-list builds alternating over the two buffers never regrow them
-    const int rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par],
-                        std::max(n_packets, n_events / EMVS_PACKET_SIZE + 1) * sizeof(emvs_packet));
-    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], packets, n_packets * sizeof(emvs_packet), cudaMemcpyHostToDevice,
                              ctx->copy_stream));
     CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
@@ -1452,6 +1558,24 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
   // (voting is a sum over events, so head + tail == whole list up to float summation order; the per-plane
   // counters add exactly).  When the stream is busy (the previous camera is still voting) the whole upload is
   // already hidden and the list is built in one piece.  The slab-wise exchanges need final slabs: no split.
+  if (ctx->prefetch.valid && ctx->prefetch.has_packets && ctx->prefetch.host == events && ctx->prefetch.n == n_events &&
+      ctx->prefetch.mapper == m && ctx->prefetch.traj == traj && ctx->prefetch.n_poses == n_poses &&
+      std::memcmp(&ctx->prefetch.T_rv_w, T_rv_w, sizeof(emvs_pose)) == 0) {
+    // emvs_mapper_prefetch_dsi ran for exactly this call: events and packets are in HBM (or landing), only the
+    // kernels are left
+    ctx->prefetch.valid = false;
+    ctx->prefetch.has_packets = false;
+    ctx->cur_events = ctx->prefetch.buf;
+    ctx->cur_packets = ctx->prefetch.par;
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetched, 0));
+    ctx->mark_consumed = true;
+    const int rc = build_on_device(m, (const emvs_event*)ctx->d_events[ctx->cur_events], n_events,
+                                   (const emvs_packet*)ctx->d_packets[ctx->cur_packets], ctx->prefetch.n_pk, flags);
+    ctx->mark_consumed = false;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_prefetched));   // the caller may reuse `events` on return
+    return EMVS_OK;
+  }
   if (take_prefetch(ctx, events, n_events)) {
     // the list was announced earlier (emvs_context_prefetch_events): nothing to upload, the packet stage is all
     // that stands between the call and the first vote

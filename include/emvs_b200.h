@@ -165,6 +165,17 @@ EMVS_API int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, 
  * upload.  Returns immediately.  The list must stay valid and unchanged until that call has returned; one
  * prefetch can be pending per context (a new one replaces it); other lists may be built in between. */
 EMVS_API int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, size_t n_events);
+/* Device self-test of the vote kernel's shared-divisor division (a prepared reciprocal per (plane, packet) and three
+ * FFMAs per numerator instead of a full IEEE division): runs about n_pairs pseudo-random and adversarial operand
+ * pairs inside the prepared range through both and returns how many quotients differ in any bit from __fdiv_rn. */
+EMVS_API int emvs_selftest_division(emvs_context* ctx, uint64_t n_pairs, uint32_t seed, uint64_t* mismatches);
+/* The same for a whole later emvs_mapper_evaluate_dsi call: the event upload starts now AND the host packet stage
+ * runs now (in the calling thread, while the device is busy with earlier work), its packets follow the events to
+ * the device.  The later emvs_mapper_evaluate_dsi[_flags] call with the same (mapper, events, n_events, traj, n_poses,
+ * *T_rv_w) only launches kernels; with any other arguments it falls back to what emvs_context_prefetch_events gives
+ * (or to the ordinary path).  `events` and `traj` must stay valid and unchanged until that call has returned. */
+EMVS_API int emvs_mapper_prefetch_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                             const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w);
 /* Number of kernels this library launched on the context so far (bench `gpu_launches`). */
 EMVS_API int emvs_context_launch_count(emvs_context* ctx, uint64_t* out);
 /* Per-launch device timing of the vote kernel (the dominant kernel; bench.py's roofline):

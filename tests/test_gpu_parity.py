@@ -163,6 +163,65 @@ def test_prefetch_events(ctx, small_case, built_small):
             m.close()
 
 
+def test_prefetch_dsi(ctx, small_case, built_small):
+    """MapperEMVS.prefetch runs the upload and the host packet stage of a later evaluateDSI ahead of time; the later
+    call with the same arguments only launches kernels, any other call falls back."""
+    import time
+    _, oracle = built_small
+    trs = [api.LinearTrajectory(t) for t in small_case.trajs]
+    ms = [api.MapperEMVS(ctx, c, small_case.shape) for c in small_case.cams[:2]]
+    m0b = api.MapperEMVS(ctx, small_case.cams[0], small_case.shape)
+    pinned = []
+    for i in range(2):
+        buf = api.pinned_empty(small_case.events[i].shape, small_case.events[i].dtype)
+        buf[...] = small_case.events[i]
+        pinned.append(buf)
+
+    def check(m, i):
+        assert np.array_equal(m.counts(), oracle[i][1])
+        np.testing.assert_allclose(m.dsi_.download(), oracle[i][0], rtol=DSI_RTOL, atol=DSI_ATOL)
+    try:
+        # white box: after the prefetch has landed, destroy coordinates AND timestamps on the host; only a call that
+        # uses the prefetched events and the prefetched packets can still produce the right DSI
+        ms[0].prefetch(pinned[0], trs[0], small_case.T_rv_w)
+        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)      # unrelated builds in between
+        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)      # (twice: both avoid the reserved packet buffer)
+        time.sleep(0.2)
+        saved = pinned[0].copy()
+        pinned[0]["x"] = 0
+        pinned[0]["sec"] = 0
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+        pinned[0][...] = saved
+        check(ms[0], 0); check(ms[1], 1)
+        # another mapper than the one announced: falls back to the prefetched events + its own packet stage
+        ms[0].prefetch(pinned[0], trs[0], small_case.T_rv_w)
+        assert m0b.evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+        check(m0b, 0)
+        # steady state of a streaming caller
+        for _ in range(3):
+            assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+            assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)
+            ms[0].prefetch(pinned[0], trs[0], small_case.T_rv_w)
+            api.fuse_collapse([m.dsi_ for m in ms], 2, ms[0].raw_depths_vec_)
+            check(ms[0], 0); check(ms[1], 1)
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+        check(ms[0], 0)
+        # fewer than 1024 events: nothing is prefetched, the later call returns False as always
+        ms[0].prefetch(pinned[0][:1000].copy(), trs[0], small_case.T_rv_w)
+        assert ms[0].evaluateDSI(pinned[0][:1000], trs[0], small_case.T_rv_w) is False
+    finally:
+        for m in ms + [m0b]:
+            m.close()
+
+
+def test_prepared_division_is_ieee(ctx):
+    """The vote kernel's shared-divisor division (prepared reciprocal + 3 FFMAs per numerator, EMVS_VOTE_FASTDIV)
+    must equal __fdiv_rn bit for bit over its whole operand range: device self-test over ~2^30 random and adversarial
+    pairs (all-ones / power-of-two mantissas, exact and one-ulp-off multiples of the divisor)."""
+    for seed in (1, 2, 3, 4):
+        assert ctx.selftest_division(1 << 28, seed) == 0
+
+
 def test_mean_square(built_small, O):
     mappers, oracle = built_small
     for m, (dsi_o, _) in zip(mappers, oracle):
