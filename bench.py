@@ -44,7 +44,8 @@ if ROOT not in sys.path:
 
 METRIC = "Mevents/s DSI build + fuse + argmax @ 640x480x256 (depth-map ms reported beside)"
 UNIT = "Mevents/s"
-WORKLOAD = "dsec_stereo"
+WORKLOAD = "dsec_stereo"          # BASELINE.json configs[1]; --workload bar4 selects configs[2] (4 cameras, 10 M events each, GM)
+FUSION_NAMES = {1: "min", 2: "harmonic", 3: "geometric", 4: "arithmetic", 5: "rms", 6: "max"}
 
 
 def parse_args():
@@ -53,7 +54,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--events-per-cam", type=int, default=5_000_000)
+    ap.add_argument("--workload", default="dsec_stereo", choices=["dsec_stereo", "bar4"],
+                    help="dsec_stereo = BASELINE.json configs[1] (the metric's configuration); bar4 = configs[2]")
+    ap.add_argument("--events-per-cam", type=int, default=0, help="default: 5 M (dsec_stereo), 10 M (bar4)")
     ap.add_argument("--kind", default="structured", choices=["structured", "uniform"])
     ap.add_argument("--cpu-sample-events", type=int, default=5_000_000,
                     help="events per camera of the bounded CPU-baseline sample")
@@ -64,7 +67,13 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU DSI exchange: fused reduce+fuse+argmax over NVLink peer memory, or "
                          "slab-wise ncclAllReduce overlapped with voting followed by a local sweep")
-    return ap.parse_args()
+    a = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = a.workload
+    if not a.events_per_cam:
+        a.events_per_cam = 5_000_000 if a.workload == "dsec_stereo" else 10_000_000
+    a.cpu_sample_events = min(a.cpu_sample_events, a.events_per_cam)
+    return a
 
 
 def load_peaks():
@@ -211,7 +220,8 @@ def run_reference(args):
         if i >= args.warmup and sum(vals) > 240:   # keep the whole run within a few minutes
             break
     t = float(np.mean(vals))
-    n_cams = 2
+    n_cams = len(_CPU_WORKLOAD[next(iter(_CPU_WORKLOAD))][1])
+    method = _CPU_WORKLOAD[next(iter(_CPU_WORKLOAD))][5]
     value = n_cams * n_full / t / 1e6
     last["value"] = value
     _emit(json.dumps({
@@ -219,7 +229,7 @@ def run_reference(args):
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "events_per_camera": n_full, "cameras": n_cams, "dsi": [640, 480, 256],
-                   "fusion": "harmonic", "event_distribution": args.kind},
+                   "fusion": FUSION_NAMES[method], "event_distribution": args.kind},
         "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -441,7 +451,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "description": desc, "events_per_camera_per_gpu": n_ev, "cameras": n_cams,
-                       "dsi": [dimX, dimY, dimZ], "fusion": "harmonic", "event_distribution": args.kind,
+                       "dsi": [dimX, dimY, dimZ], "fusion": FUSION_NAMES[method], "event_distribution": args.kind,
                        "sharding": ("none" if world == 1 else
                                     "event sub-interval per GPU; slab-wise reduce of each GPU's row band over NVLink peer memory under the votes, then fuse+argmax of the band and peer stores of the maps"
                                     if peer is not None else
