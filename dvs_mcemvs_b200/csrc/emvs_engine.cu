@@ -1350,6 +1350,12 @@ int emvs_mapper_destroy(emvs_mapper* m)
   if (!m) return EMVS_OK;
   DeviceGuard guard(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  // packets prefetched for this mapper must not be matched by a later mapper allocated at the same address
+  // (the prefetched events stay usable: they do not depend on the mapper)
+  if (m->ctx->prefetch.mapper == m) {
+    m->ctx->prefetch.has_packets = false;
+    m->ctx->prefetch.mapper = nullptr;
+  }
   emvs_grid_destroy(m->grid);
   cudaFree(m->d_depths);
   cudaFree(m->d_lut);
