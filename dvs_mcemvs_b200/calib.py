@@ -1,0 +1,212 @@
+"""Stereo-rig calibration loaders of the mapping path's callers, ROS-free.
+
+The reference fills two image_geometry::PinholeCameraModel objects plus the extrinsics `mat4_1_0` / `matR_L`
+(right-from-left) and the hand-eye transform (mapper_emvs_stereo/src/calib.cpp); the mapper then reads the
+projection-matrix intrinsics and builds its rectification LUT from K, D, R, P (mapper_emvs_stereo.cpp:29-64, 256-299).
+Here the same inputs produce `api.CameraModel`s (projection intrinsics + the LUT, via `emvs_rectify_lut` — bit-exact
+against OpenCV, tests/test_rectify_lut.py) and 4x4 float64 matrices.
+
+  dsec_yaml(cam_to_cam.yaml, cam_to_lidar.yaml)    get_camera_calib_dsec_yaml           calib.cpp:365-457
+  dsec_zurich04a(), dsec_interlaken00b()           the two hard-coded DSEC rigs         calib.cpp:459-589
+  kalibr_yaml(camchain.yaml[, hand_eye.json])      get_camera_calib_sony                calib.cpp:31-138
+
+Conventions kept literally: the rectification rotation is ignored (R = I: "work on unrectified images"); when the file
+has no projection matrix, P = cv::getOptimalNewCameraMatrix(K, D, size, alpha = 0); BOTH cameras get camera 0's P;
+"none" distortion becomes plumb_bob with zero coefficients; get_camera_calib_sony hands camera_info[0] to cam1 and
+camera_info[1] to cam0 (calib.cpp:106-108) and inverts T_cn_cnm1.
+"""
+import json
+
+import numpy as np
+
+from .api import CameraModel
+
+
+class StereoCalib:
+    """cam0 / cam1: api.CameraModel; mat_1_0: 4x4 right-from-left (the reference's mat4_1_0 / matR_L);
+    mat_hand_eye: 4x4 or None; info: the sensor_msgs/CameraInfo-like dicts the cameras were built from."""
+
+    def __init__(self, cam0, cam1, mat_1_0, mat_hand_eye, info):
+        self.cam0, self.cam1, self.mat_1_0, self.mat_hand_eye, self.info = cam0, cam1, mat_1_0, mat_hand_eye, info
+
+
+def _cv2():
+    try:
+        import cv2
+    except ImportError as e:
+        raise RuntimeError("calibration without a projection matrix needs OpenCV (cv2.getOptimalNewCameraMatrix)") from e
+    return cv2
+
+
+def optimal_projection(K, D, width, height):
+    """P = [getOptimalNewCameraMatrix(K, D, (w, h), 0) | 0] — calib.cpp:92-99, 399-405, 475-481."""
+    Kn = _cv2().getOptimalNewCameraMatrix(np.asarray(K, np.float64).reshape(3, 3), np.asarray(D, np.float64), (int(width), int(height)), 0)
+    if isinstance(Kn, tuple):
+        Kn = Kn[0]
+    P = np.zeros((3, 4), np.float64)
+    P[:, :3] = Kn
+    return P
+
+
+def _info(width, height, fx, fy, cx, cy, model, D):
+    if model == "none":
+        model, D = "plumb_bob", [0.0] * 5
+    elif model == "radtan":
+        model = "plumb_bob"
+    elif model == "equidistant":
+        model = "fisheye"
+    elif model not in ("plumb_bob", "fisheye"):
+        raise ValueError(f"unknown distortion model {model!r}")
+    return dict(width=int(width), height=int(height), K=np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64),
+                D=np.asarray(D, np.float64), R=np.eye(3), distortion_model=model, P=None)
+
+
+def _camera(info):
+    return CameraModel.from_camera_info(info["width"], info["height"], info["K"], info["D"], info["R"], info["P"],
+                                        info["distortion_model"])
+
+
+def _mat4(node):
+    m = np.asarray(node, np.float64)
+    if m.shape != (4, 4):
+        raise ValueError(f"expected a 4x4 matrix, got shape {m.shape}")
+    return m
+
+
+def _rot4(node):
+    m = np.eye(4)
+    m[:3, :3] = np.asarray(node, np.float64).reshape(3, 3)
+    return m
+
+
+def _load_yaml(path):
+    import yaml
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+def dsec_yaml(calib_path, mocap_calib_path=None, event_cam_ids=(0, 3)):
+    """DSEC cam_to_cam.yaml (+ cam_to_lidar.yaml): event cameras 0 and 3, matR_L = T_32 T_21 T_10,
+    hand-eye = T_lidar_camRect1 * R_rect1 * T_10 (calib.cpp:365-457)."""
+    c = _load_yaml(calib_path)
+    infos = []
+    for cid in event_cam_ids:
+        cam = c["intrinsics"][f"cam{cid}"]
+        fx, fy, cx, cy = (float(v) for v in cam["camera_matrix"])
+        model = cam["distortion_model"]
+        D = [float(v) for v in cam.get("distortion_coeffs", [])][:4]
+        infos.append(_info(cam["resolution"][0], cam["resolution"][1], fx, fy, cx, cy, model, D))
+    infos[0]["P"] = optimal_projection(infos[0]["K"], infos[0]["D"], infos[0]["width"], infos[0]["height"])
+    # the reference computes camera 1's own P and then overwrites it with camera 0's (calib.cpp:408-410)
+    infos[1]["P"] = infos[0]["P"]
+    ext = c["extrinsics"]
+    T_10, T_21, T_32 = _mat4(ext["T_10"]), _mat4(ext["T_21"]), _mat4(ext["T_32"])
+    mat_R_L = T_32 @ T_21 @ T_10
+    hand_eye = None
+    if mocap_calib_path:
+        T_lidar_camRect1 = _mat4(_load_yaml(mocap_calib_path)["T_lidar_camRect1"])
+        hand_eye = T_lidar_camRect1 @ _rot4(ext["R_rect1"]) @ T_10
+    return StereoCalib(_camera(infos[0]), _camera(infos[1]), mat_R_L, hand_eye, infos)
+
+
+_DSEC_RIGS = {
+    # K (fx, fy, cx, cy) and D of event cameras 0 / 3, then T_10, T_21, T_32, T_lidar_camRect1, R_rect1 (calib.cpp:459-589)
+    "zurich_city_04_a": dict(
+        K=[(553.4686750102932, 553.3994078799127, 346.65339162053317, 216.52092103243012),
+           (552.1819422959984, 551.4454720096484, 336.87432177064744, 226.32630571403274)],
+        D=[(-0.09356476362537607, 0.19445779814646236, 7.642434980998821e-05, 0.0019563864604273664),
+           (-0.09493681546997375, 0.2021148065491477, 0.0005821287651820125, 0.0014552921745527136)],
+        T_10=[[0.9997329831508507, 0.00994674446197701, 0.020857245142004693, -0.043722240320426424],
+              [-0.01003579267550241, 0.999940949009329, 0.004169095789442527, 0.0010155694745410755],
+              [-0.020814544570561252, -0.004377301558648307, 0.9997737713930034, -0.013372668558381158], [0, 0, 0, 1]],
+        T_21=[[0.9998379578286035, -0.017926384876108554, 0.0016440226264295469, -0.5092603987305321],
+              [0.017914084504235202, 0.9998135043384297, 0.007214022378586629, -0.0022179629729152214],
+              [-0.0017730373650056029, -0.007183402242479184, 0.9999726271607238, 0.0042971588717280644], [0, 0, 0, 1]],
+        T_32=[[0.9999876185667624, -0.0034167786978265787, -0.0036177806040117192, -0.046041759529914676],
+              [0.0033579259589126046, 0.9998639316478117, -0.016150619896091543, -0.0011068440180470077],
+              [0.0036724714325840242, 0.01613827168886575, 0.9998630251891839, 0.012672727774474509], [0, 0, 0, 1]],
+        T_lidar_camRect1=[[0.006502250714427837, 0.0016414391549515739, 0.9999775129537399, 0.448],
+                          [-0.9996294044397522, 0.026445536238290795, 0.006456577459882262, 0.255],
+                          [-0.026434343477244382, -0.999648908012493, 0.0018127863517872211, -0.215], [0, 0, 0, 1]],
+        R_rect1=[[0.9998858610925897, -0.013510711178262034, -0.006762061119800281],
+                 [0.013535205789223095, 0.9999019509726164, 0.0035897974036225495],
+                 [0.00671289739037555, -0.0036809135568848755, 0.9999706935125713]]),
+    "interlaken_00_b": dict(
+        K=[(555.6627242364661, 555.8306341927942, 342.5725306057865, 215.26831427862848),
+           (553.800041834315, 553.7026022383894, 333.21860953836267, 226.01033624096638)],
+        D=[(-0.09094341408134071, 0.18339771556281387, -0.0006982341741678465, 0.00041396758898911876),
+           (-0.09492592983896557, 0.20394312250370014, 0.00033282360055722797, -0.001101242451777801)],
+        T_10=[[0.9996874046885865, 0.009652146488870916, 0.023063585478994113, -0.04410263392688484],
+              [-0.009722042371104245, 0.9999484753460813, 0.0029203673010648615, 0.0005281285423087664],
+              [-0.023034209322743096, -0.0031436795631953228, 0.9997297347181744, -0.01229891454144492], [0, 0, 0, 1]],
+        T_21=[[0.9998543808844597, -0.01706309861700861, -0.00026017635946350924, -0.5094961871754736],
+              [0.017064416377671962, 0.9998338346058513, 0.00641162000174109, -0.002022496204233391],
+              [0.0001507310227716978, -0.006415126105036775, 0.9999794115066636, 0.005365297617411473], [0, 0, 0, 1]],
+        T_32=[[0.9999880111304372, -0.003533401537847065, -0.003390083916194203, -0.04551026028184807],
+              [0.003476600244706753, 0.9998558803824363, -0.016617211420558598, -0.001048727690114844],
+              [0.0034483106189848347, 0.016605226232405814, 0.999856177465359, 0.013554100781902953], [0, 0, 0, 1]],
+        T_lidar_camRect1=[[0.01539728189227399, -0.0012823052573279758, 0.9998806325774878, 0.448],
+                          [-0.9996610000153124, 0.020978176075891836, 0.015420803380972237, 0.255],
+                          [-0.02099544614233234, -0.9997791115150167, -0.0009588636652390625, -0.215], [0, 0, 0, 1]],
+        R_rect1=[[0.9998572179847892, -0.013025778024398856, -0.010764420587133948],
+                 [0.013060715513432202, 0.9999096430275752, 0.003181743349841093],
+                 [0.01072200326407413, -0.0033218800890692088, 0.9999369998948329]]),
+}
+
+
+def _dsec_builtin(name):
+    r = _DSEC_RIGS[name]
+    infos = [_info(640, 480, *r["K"][i], "plumb_bob", r["D"][i]) for i in range(2)]
+    infos[0]["P"] = optimal_projection(infos[0]["K"], infos[0]["D"], 640, 480)
+    infos[1]["P"] = infos[0]["P"]          # camera_info.P is not recomputed for the second camera (calib.cpp:485-490)
+    T_10, T_21, T_32 = (_mat4(r[k]) for k in ("T_10", "T_21", "T_32"))
+    hand_eye = _mat4(r["T_lidar_camRect1"]) @ _rot4(r["R_rect1"]) @ T_10
+    return StereoCalib(_camera(infos[0]), _camera(infos[1]), T_32 @ T_21 @ T_10, hand_eye, infos)
+
+
+def dsec_zurich04a():
+    """get_camera_calib_dsec_zurich04a (calib.cpp:459-521)."""
+    return _dsec_builtin("zurich_city_04_a")
+
+
+def dsec_interlaken00b():
+    """get_camera_calib_dsec_interlaken00b (calib.cpp:525-587)."""
+    return _dsec_builtin("interlaken_00_b")
+
+
+def _quat_to_rot(w, x, y, z):
+    n = np.sqrt(w * w + x * x + y * y + z * z)
+    w, x, y, z = w / n, x / n, y / n, z / n
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], np.float64)
+
+
+def kalibr_yaml(calib_path, mocap_calib_path=None):
+    """Kalibr camchain (cam0 / cam1 with `intrinsics`, `distortion_model`, `distortion_coeffs`, `resolution`, optional
+    `projection_matrix`, cam1.T_cn_cnm1) + optional hand-eye JSON {rotation: {w,i,j,k}, translation: {x,y,z}} —
+    get_camera_calib_sony (calib.cpp:31-138), including its camera swap and the inverted extrinsics."""
+    c = _load_yaml(calib_path)
+    infos = []
+    for i in range(2):
+        cam = c[f"cam{i}"]
+        fx, fy, cx, cy = (float(v) for v in cam["intrinsics"])
+        info = _info(cam["resolution"][0], cam["resolution"][1], fx, fy, cx, cy, cam["distortion_model"],
+                     [float(v) for v in cam.get("distortion_coeffs", [])])
+        if cam.get("projection_matrix") is not None:
+            info["P"] = np.asarray(cam["projection_matrix"], np.float64).reshape(3, 4)
+        else:
+            info["P"] = optimal_projection(info["K"], info["D"], info["width"], info["height"])
+        infos.append(info)
+    infos[1]["P"] = infos[0]["P"]
+    cam1, cam0 = _camera(infos[0]), _camera(infos[1])          # sic: calib.cpp:106-108
+    mat_1_0 = np.linalg.inv(_mat4(c["cam1"]["T_cn_cnm1"]))
+    hand_eye = None
+    if mocap_calib_path:
+        with open(mocap_calib_path) as f:
+            m = json.load(f)
+        hand_eye = np.eye(4)
+        r, t = m["rotation"], m["translation"]
+        hand_eye[:3, :3] = _quat_to_rot(float(r["w"]), float(r["i"]), float(r["j"]), float(r["k"]))
+        hand_eye[:3, 3] = [float(t["x"]), float(t["y"]), float(t["z"])]
+    return StereoCalib(cam0, cam1, mat_1_0, hand_eye, infos)

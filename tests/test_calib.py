@@ -1,0 +1,98 @@
+"""Calibration loaders (calib.cpp:31-138, 365-589): no GPU needed — the LUT comes from the
+library's host-side emvs_rectify_lut."""
+import json
+
+import numpy as np
+import pytest
+
+from dvs_mcemvs_b200 import calib, synth
+
+cv2 = pytest.importorskip("cv2")
+yaml = pytest.importorskip("yaml")
+
+
+def test_dsec_zurich04a_matches_the_bench_rig():
+    c = calib.dsec_zurich04a()
+    rig = synth.rig_dsec()
+    for a, b in zip((c.cam0, c.cam1), rig.cams):
+        assert (a.width, a.height) == (640, 480)
+        assert (a.fx, a.fy, a.cx, a.cy) == (b.fx, b.fy, b.cx, b.cy)
+        assert a.lut.tobytes() == b.lut.tobytes()
+    # both cameras share camera 0's projection matrix; the event cameras sit ~0.6 m apart along x
+    assert (c.cam0.fx, c.cam0.cx) == (c.cam1.fx, c.cam1.cx)
+    assert c.mat_1_0[0, 3] == pytest.approx(-0.599, abs=2e-3) and abs(c.mat_1_0[1, 3]) < 5e-3
+    np.testing.assert_allclose(c.mat_1_0[:3, :3] @ c.mat_1_0[:3, :3].T, np.eye(3), atol=1e-9)
+    assert c.mat_hand_eye.shape == (4, 4) and c.mat_hand_eye[3].tolist() == [0, 0, 0, 1]
+    # LUT against OpenCV for a few raw pixels (image_geometry::rectifyPoint == undistortPoints with R, P)
+    info = c.info[1]
+    pts = np.array([[[0.0, 0.0]], [[639.0, 479.0]], [[320.0, 240.0]], [[17.0, 401.0]]], np.float64)
+    want = cv2.undistortPoints(pts, info["K"], info["D"], R=info["R"], P=info["P"]).reshape(-1, 2)
+    got = np.array([c.cam1.lut[int(y) * 640 + int(x)] for x, y in pts.reshape(-1, 2)])
+    np.testing.assert_allclose(got, want.astype(np.float32), rtol=0, atol=1e-4)
+
+
+def _dsec_yaml_files(tmp_path, rig):
+    r = calib._DSEC_RIGS[rig]
+
+    def cam(i, kind="event"):
+        return dict(camera_type=kind, camera_matrix=list(r["K"][i]), distortion_coeffs=list(r["D"][i]),
+                    distortion_model="radtan", resolution=[640, 480])
+    doc = dict(intrinsics=dict(cam0=cam(0), cam1=cam(0, "frame"), cam2=cam(1, "frame"), cam3=cam(1)),
+               extrinsics=dict(T_10=r["T_10"], T_21=r["T_21"], T_32=r["T_32"], R_rect1=r["R_rect1"]))
+    p = tmp_path / "cam_to_cam.yaml"
+    p.write_text(yaml.safe_dump(doc))
+    q = tmp_path / "cam_to_lidar.yaml"
+    q.write_text(yaml.safe_dump(dict(T_lidar_camRect1=r["T_lidar_camRect1"])))
+    return str(p), str(q)
+
+
+@pytest.mark.parametrize("rig,builtin", [("zurich_city_04_a", calib.dsec_zurich04a), ("interlaken_00_b", calib.dsec_interlaken00b)])
+def test_dsec_yaml_equals_hard_coded_rig(tmp_path, rig, builtin):
+    p, q = _dsec_yaml_files(tmp_path, rig)
+    a, b = calib.dsec_yaml(p, q), builtin()
+    for x, y in ((a.cam0, b.cam0), (a.cam1, b.cam1)):
+        assert (x.fx, x.fy, x.cx, x.cy) == (y.fx, y.fy, y.cx, y.cy) and x.lut.tobytes() == y.lut.tobytes()
+    assert np.array_equal(a.mat_1_0, b.mat_1_0) and np.array_equal(a.mat_hand_eye, b.mat_hand_eye)
+    assert calib.dsec_yaml(p).mat_hand_eye is None            # no cam_to_lidar file: extrinsics only
+
+
+def test_kalibr_yaml_swap_inverse_fisheye_and_hand_eye(tmp_path):
+    T = np.eye(4)
+    T[:3, 3] = [-0.1, 0.002, 0.001]
+    c, s = np.cos(0.01), np.sin(0.01)
+    T[:3, :3] = [[c, 0, s], [0, 1, 0], [-s, 0, c]]
+    doc = dict(cam0=dict(intrinsics=[300.0, 301.0, 170.0, 130.0], distortion_model="equidistant",
+                         distortion_coeffs=[-0.02, 0.01, -0.003, 0.001], resolution=[346, 260]),
+               cam1=dict(intrinsics=[299.0, 300.0, 172.0, 128.0], distortion_model="none", resolution=[346, 260],
+                         T_cn_cnm1=T.tolist()))
+    p = tmp_path / "camchain.yaml"
+    p.write_text(yaml.safe_dump(doc))
+    h = tmp_path / "hand_eye.json"
+    h.write_text(json.dumps(dict(rotation=dict(w="0.5", i="0.5", j="0.5", k="0.5"), translation=dict(x="0.1", y="0.2", z="0.3"))))
+    r = calib.kalibr_yaml(str(p), str(h))
+    # sic: cam1 is built from camera_info[0] (the fisheye one), cam0 from camera_info[1] (zero distortion -> identity LUT)
+    ident = np.stack(np.meshgrid(np.arange(346, dtype=np.float32), np.arange(260, dtype=np.float32)), -1).reshape(-1, 2)
+    info0 = r.info[0]
+    assert info0["distortion_model"] == "fisheye" and r.info[1]["distortion_model"] == "plumb_bob"
+    # camera 1 of the file has zero distortion: image_geometry's rectifyPoint returns the raw pixel (distortion state
+    # NONE) although its K differs from the shared P — the LUT is the identity
+    P = info0["P"]
+    assert np.array_equal(r.cam0.lut, ident)
+    pts = np.array([[[10.0, 20.0]], [[300.0, 200.0]], [[173.0, 130.0]]], np.float32)
+    want1 = cv2.fisheye.undistortPoints(pts, info0["K"], info0["D"], R=np.eye(3), P=P).reshape(-1, 2)
+    got1 = np.array([r.cam1.lut[int(y) * 346 + int(x)] for x, y in pts.reshape(-1, 2)])
+    np.testing.assert_allclose(got1, want1, atol=1e-3)
+    assert (r.cam0.fx, r.cam0.cx) == (r.cam1.fx, r.cam1.cx) == (P[0, 0], P[0, 2])
+    np.testing.assert_allclose(r.mat_1_0 @ T, np.eye(4), atol=1e-12)
+    # quaternion (0.5, 0.5, 0.5, 0.5) is the cyclic permutation x -> y -> z -> x
+    np.testing.assert_allclose(r.mat_hand_eye[:3, :3], [[0, 0, 1], [1, 0, 0], [0, 1, 0]], atol=1e-12)
+    assert r.mat_hand_eye[:3, 3].tolist() == [0.1, 0.2, 0.3]
+    # a projection matrix in the file is used as it is
+    doc["cam0"]["projection_matrix"] = [[250.0, 0, 173.0, 0], [0, 250.0, 130.0, 0], [0, 0, 1, 0]]
+    p.write_text(yaml.safe_dump(doc))
+    r2 = calib.kalibr_yaml(str(p))
+    assert (r2.cam0.fx, r2.cam0.fy, r2.cam0.cx, r2.cam0.cy) == (250.0, 250.0, 173.0, 130.0) and r2.mat_hand_eye is None
+    doc["cam0"]["distortion_model"] = "kannala_brandt_9"
+    p.write_text(yaml.safe_dump(doc))
+    with pytest.raises(ValueError):
+        calib.kalibr_yaml(str(p))
