@@ -1559,12 +1559,6 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
     ctx->h_packets_cap = max_pk;
   }
   REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi: rectification LUT not set (emvs_mapper_set_lut)");
-  // Split upload.  When the pipeline is idle nothing hides this call's event upload (80 MB per 5 M events, ~1.6 ms
-  // over PCIe 5): upload and vote the HEAD of the list first (a build of its packets), and let the TAIL cross
-  // PCIe under the head's vote kernels; the tail is then voted with EMVS_BUILD_ACCUMULATE into the same DSI
-  // (voting is a sum over events, so head + tail == whole list up to float summation order; the per-plane
-  // counters add exactly).  When the stream is busy (the previous camera is still voting) the whole upload is
-  // already hidden and the list is built in one piece.  The slab-wise exchanges need final slabs: no split.
   if (ctx->prefetch.valid && ctx->prefetch.has_packets && ctx->prefetch.host == events && ctx->prefetch.n == n_events &&
       ctx->prefetch.mapper == m && ctx->prefetch.traj == traj && ctx->prefetch.n_poses == n_poses &&
       std::memcmp(&ctx->prefetch.T_rv_w, T_rv_w, sizeof(emvs_pose)) == 0) {
@@ -1593,6 +1587,12 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
     if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return EMVS_OK;
   }
+  // Split upload.  When the pipeline is idle nothing hides this call's event upload (80 MB per 5 M events, ~1.6 ms
+  // over PCIe 5): upload and vote the HEAD of the list first (a build of its packets), and let the TAIL cross
+  // PCIe under the head's vote kernels; the tail is then voted with EMVS_BUILD_ACCUMULATE into the same DSI
+  // (voting is a sum over events, so head + tail == whole list up to float summation order; the per-plane
+  // counters add exactly).  When the stream is busy (the previous camera is still voting) the whole upload is
+  // already hidden and the list is built in one piece.  The slab-wise exchanges need final slabs: no split.
   const bool exchange = (flags & (EMVS_BUILD_ALLREDUCE | EMVS_BUILD_PEER_REDUCE)) != 0;
   size_t n_head = 0;
   if (ctx->split_percent && !exchange && n_events >= ctx->split_min_events && n_events >= 4 * (size_t)EMVS_PACKET_SIZE) {
