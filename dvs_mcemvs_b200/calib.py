@@ -9,6 +9,9 @@ against OpenCV, tests/test_rectify_lut.py) and 4x4 float64 matrices.
   dsec_yaml(cam_to_cam.yaml, cam_to_lidar.yaml)    get_camera_calib_dsec_yaml           calib.cpp:365-457
   dsec_zurich04a(), dsec_interlaken00b()           the two hard-coded DSEC rigs         calib.cpp:459-589
   kalibr_yaml(camchain.yaml[, hand_eye.json])      get_camera_calib_sony                calib.cpp:31-138
+  kalibr_yaml_mvsec / kalibr_yaml_m3ed             get_camera_calib_yaml_mvsec / _m3ed  calib.cpp:141-228, 811-885
+  esim_yaml(rig.yaml)                              get_camera_calib_yaml                calib.cpp:231-267
+  basalt_json(calib.json[, mocap.json])            get_camera_calib_json (TUM-VIE)      calib.cpp:271-361
 
 Conventions kept literally: the rectification rotation is ignored (R = I: "work on unrectified images"); when the file
 has no projection matrix, P = cv::getOptimalNewCameraMatrix(K, D, size, alpha = 0); BOTH cameras get camera 0's P;
@@ -182,11 +185,7 @@ def _quat_to_rot(w, x, y, z):
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], np.float64)
 
 
-def kalibr_yaml(calib_path, mocap_calib_path=None):
-    """Kalibr camchain (cam0 / cam1 with `intrinsics`, `distortion_model`, `distortion_coeffs`, `resolution`, optional
-    `projection_matrix`, cam1.T_cn_cnm1) + optional hand-eye JSON {rotation: {w,i,j,k}, translation: {x,y,z}} —
-    get_camera_calib_sony (calib.cpp:31-138), including its camera swap and the inverted extrinsics."""
-    c = _load_yaml(calib_path)
+def _kalibr_infos(c):
     infos = []
     for i in range(2):
         cam = c[f"cam{i}"]
@@ -199,14 +198,86 @@ def kalibr_yaml(calib_path, mocap_calib_path=None):
             info["P"] = optimal_projection(info["K"], info["D"], info["width"], info["height"])
         infos.append(info)
     infos[1]["P"] = infos[0]["P"]
+    return infos
+
+
+def _pose4(qw, qx, qy, qz, px, py, pz):
+    m = np.eye(4)
+    m[:3, :3] = _quat_to_rot(float(qw), float(qx), float(qy), float(qz))
+    m[:3, 3] = [float(px), float(py), float(pz)]
+    return m
+
+
+def kalibr_yaml(calib_path, mocap_calib_path=None):
+    """Kalibr camchain (cam0 / cam1 with `intrinsics`, `distortion_model`, `distortion_coeffs`, `resolution`, optional
+    `projection_matrix`, cam1.T_cn_cnm1) + optional hand-eye JSON {rotation: {w,i,j,k}, translation: {x,y,z}} —
+    get_camera_calib_sony (calib.cpp:31-138), including its camera swap and the inverted extrinsics."""
+    c = _load_yaml(calib_path)
+    infos = _kalibr_infos(c)
     cam1, cam0 = _camera(infos[0]), _camera(infos[1])          # sic: calib.cpp:106-108
     mat_1_0 = np.linalg.inv(_mat4(c["cam1"]["T_cn_cnm1"]))
     hand_eye = None
     if mocap_calib_path:
         with open(mocap_calib_path) as f:
             m = json.load(f)
-        hand_eye = np.eye(4)
         r, t = m["rotation"], m["translation"]
-        hand_eye[:3, :3] = _quat_to_rot(float(r["w"]), float(r["i"]), float(r["j"]), float(r["k"]))
-        hand_eye[:3, 3] = [float(t["x"]), float(t["y"]), float(t["z"])]
+        hand_eye = _pose4(r["w"], r["i"], r["j"], r["k"], t["x"], t["y"], t["z"])
     return StereoCalib(cam0, cam1, mat_1_0, hand_eye, infos)
+
+
+def kalibr_yaml_mvsec(calib_path):
+    """The same camchain format read the way get_camera_calib_yaml_mvsec / get_camera_calib_yaml_m3ed do
+    (calib.cpp:141-228, 811-885): cameras in file order, mat4_1_0 = T_cn_cnm1 as it is, identity hand-eye."""
+    c = _load_yaml(calib_path)
+    infos = _kalibr_infos(c)
+    return StereoCalib(_camera(infos[0]), _camera(infos[1]), _mat4(c["cam1"]["T_cn_cnm1"]), np.eye(4), infos)
+
+
+kalibr_yaml_m3ed = kalibr_yaml_mvsec
+
+
+def esim_yaml(calib_path):
+    """ESIM / rpg rig file: cameras[i].camera {image_width, image_height, intrinsics.data [fx,fy,cx,cy],
+    distortion.type} and cameras[i].T_B_C.data (row-major 4x4) — get_camera_calib_yaml (calib.cpp:231-267): both
+    cameras are the LEFT one with P = K, mat4_1_0 = T_B_right^-1 T_B_left, identity hand-eye."""
+    c = _load_yaml(calib_path)
+    cams = c["cameras"]
+    left = cams[0]["camera"]
+    fx, fy, cx, cy = (float(v) for v in left["intrinsics"]["data"])
+    if left["distortion"]["type"] != "none":
+        raise ValueError("get_camera_calib_yaml only handles distortion type 'none' (the reference leaves the model unset)")
+    info = _info(left["image_width"], left["image_height"], fx, fy, cx, cy, "none", [])
+    info["P"] = np.array([[fx, 0, cx, 0], [0, fy, cy, 0], [0, 0, 1, 0]], np.float64)
+    T_B_left = np.asarray(cams[0]["T_B_C"]["data"], np.float64).reshape(4, 4)
+    T_B_right = np.asarray(cams[1]["T_B_C"]["data"], np.float64).reshape(4, 4)
+    return StereoCalib(_camera(info), _camera(info), np.linalg.inv(T_B_right) @ T_B_left, np.eye(4), [info, dict(info)])
+
+
+def basalt_json(camera_calib_path, mocap_calib_path=None):
+    """TUM-VIE (basalt) calibration JSON: value0.{resolution, intrinsics, T_imu_cam}[2..3] are the two event cameras
+    (kb4 = equidistant fisheye), P = diag(0.8 fx, 0.8 fy) around the raw principal point, mat4_1_0 =
+    T_imu_cam1^-1 T_imu_cam0, hand-eye = T_imu_marker^-1 T_imu_cam0 (or T_imu_cam0) — get_camera_calib_json
+    (calib.cpp:271-361)."""
+    with open(camera_calib_path) as f:
+        v = json.load(f)["value0"]
+    infos, T_imu_cam = [], []
+    for i in range(2):
+        res = v["resolution"][i + 2]
+        k = v["intrinsics"][i + 2]["intrinsics"]
+        if v["intrinsics"][i + 2]["camera_type"] != "kb4":
+            raise ValueError("get_camera_calib_json only handles camera_type 'kb4'")
+        info = _info(res[0], res[1], k["fx"], k["fy"], k["cx"], k["cy"], "fisheye", [k["k1"], k["k2"], k["k3"], k["k4"]])
+        # 0.8 * (float) fx: the reference scales the focal length in single precision
+        info["P"] = np.array([[0.8 * float(np.float32(k["fx"])), 0, k["cx"], 0],
+                              [0, 0.8 * float(np.float32(k["fy"])), k["cy"], 0], [0, 0, 1, 0]], np.float64)
+        infos.append(info)
+        e = v["T_imu_cam"][i + 2]
+        T_imu_cam.append(_pose4(e["qw"], e["qx"], e["qy"], e["qz"], e["px"], e["py"], e["pz"]))
+    infos[1]["P"] = infos[0]["P"]
+    mat_1_0 = np.linalg.inv(T_imu_cam[1]) @ T_imu_cam[0]
+    hand_eye = T_imu_cam[0]
+    if mocap_calib_path:
+        with open(mocap_calib_path) as f:
+            e = json.load(f)["value0"]["T_imu_marker"]
+        hand_eye = np.linalg.inv(_pose4(e["qw"], e["qx"], e["qy"], e["qz"], e["px"], e["py"], e["pz"])) @ T_imu_cam[0]
+    return StereoCalib(_camera(infos[0]), _camera(infos[1]), mat_1_0, hand_eye, infos)

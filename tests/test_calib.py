@@ -96,3 +96,55 @@ def test_kalibr_yaml_swap_inverse_fisheye_and_hand_eye(tmp_path):
     p.write_text(yaml.safe_dump(doc))
     with pytest.raises(ValueError):
         calib.kalibr_yaml(str(p))
+
+
+def test_mvsec_esim_and_basalt_loaders(tmp_path):
+    T = np.eye(4)
+    T[:3, 3] = [-0.1, 0.0, 0.0]
+    doc = dict(cam0=dict(intrinsics=[226.4, 226.1, 173.6, 133.7], distortion_model="equidistant",
+                         distortion_coeffs=[-0.048, 0.011, -0.05, 0.02], resolution=[346, 260],
+                         projection_matrix=[[199.7, 0, 177.6, 0], [0, 199.7, 126.9, 0], [0, 0, 1, 0]]),
+               cam1=dict(intrinsics=[226.1, 226.0, 174.5, 124.2], distortion_model="equidistant",
+                         distortion_coeffs=[-0.045, 0.01, -0.045, 0.018], resolution=[346, 260], T_cn_cnm1=T.tolist(),
+                         projection_matrix=[[199.7, 0, 177.6, -19.9], [0, 199.7, 126.9, 0], [0, 0, 1, 0]]))
+    p = tmp_path / "camchain.yaml"
+    p.write_text(yaml.safe_dump(doc))
+    r = calib.kalibr_yaml_mvsec(str(p))
+    assert np.array_equal(r.mat_1_0, T) and np.array_equal(r.mat_hand_eye, np.eye(4))     # not inverted, identity hand-eye
+    assert r.info[0]["D"][0] == -0.048 and r.info[1]["D"][0] == -0.045                      # cameras in file order
+    assert (r.cam1.fx, r.cam1.cx) == (199.7, 177.6)                                         # camera 0's P for both
+    assert calib.kalibr_yaml_m3ed is calib.kalibr_yaml_mvsec
+
+    TL, TR = np.eye(4), np.eye(4)
+    TR[0, 3] = 0.2
+    esim = dict(cameras=[dict(camera=dict(image_width=240, image_height=180, intrinsics=dict(data=[200.0, 200.0, 120.0, 90.0]),
+                                          distortion=dict(type="none")), T_B_C=dict(data=TL.reshape(-1).tolist())),
+                         dict(camera=dict(image_width=240, image_height=180, intrinsics=dict(data=[201.0, 201.0, 121.0, 91.0]),
+                                          distortion=dict(type="none")), T_B_C=dict(data=TR.reshape(-1).tolist()))])
+    q = tmp_path / "esim.yaml"
+    q.write_text(yaml.safe_dump(esim))
+    e = calib.esim_yaml(str(q))
+    assert (e.cam1.fx, e.cam1.cx) == (200.0, 120.0)                                         # both cameras are the LEFT one
+    assert e.mat_1_0[0, 3] == pytest.approx(-0.2) and np.array_equal(e.mat_hand_eye, np.eye(4))
+    assert e.cam0.lut[5 * 240 + 7].tolist() == [7.0, 5.0]
+
+    def cam(fx, cx, px):
+        return (dict(camera_type="kb4", intrinsics=dict(fx=fx, fy=fx + 1, cx=cx, cy=360.0, k1=0.01, k2=-0.02, k3=0.003, k4=-0.001)),
+                dict(qw=1.0, qx=0.0, qy=0.0, qz=0.0, px=px, py=0.0, pz=0.0))
+    intr, ext = zip(*[cam(700.0, 640.0, 0.0)] * 2 + [cam(1049.3, 634.0, 0.05), cam(1048.1, 641.0, 0.17)])
+    basalt = dict(value0=dict(resolution=[[1024, 1024]] * 2 + [[1280, 720]] * 2, intrinsics=list(intr), T_imu_cam=list(ext)))
+    j = tmp_path / "calib.json"
+    j.write_text(json.dumps(basalt))
+    m = tmp_path / "mocap.json"
+    m.write_text(json.dumps(dict(value0=dict(T_imu_marker=dict(qw=1.0, qx=0.0, qy=0.0, qz=0.0, px=0.0, py=0.3, pz=0.0)))))
+    b = calib.basalt_json(str(j), str(m))
+    assert (b.cam0.width, b.cam0.height) == (1280, 720)
+    assert b.cam0.fx == pytest.approx(0.8 * float(np.float32(1049.3)), rel=1e-7) and b.cam0.cx == pytest.approx(634.0)
+    assert (b.cam1.fx, b.cam1.cx) == (b.cam0.fx, b.cam0.cx)
+    assert b.mat_1_0[0, 3] == pytest.approx(0.05 - 0.17) and b.mat_hand_eye[:3, 3].tolist() == pytest.approx([0.05, -0.3, 0.0])
+    info = b.info[1]
+    pts = np.array([[[100.0, 50.0]], [[1200.0, 700.0]], [[641.0, 360.0]]], np.float32)
+    want = cv2.fisheye.undistortPoints(pts, info["K"], info["D"], R=np.eye(3), P=info["P"]).reshape(-1, 2)
+    got = np.array([b.cam1.lut[int(y) * 1280 + int(x)] for x, y in pts.reshape(-1, 2)])
+    np.testing.assert_allclose(got, want, atol=2e-3)
+    assert np.array_equal(calib.basalt_json(str(j)).mat_hand_eye[:3, 3], [0.05, 0.0, 0.0])
