@@ -7,6 +7,10 @@ mapping path consumes — no ROS installation needed.
   dvs_msgs/EventArray        -> EVENT_DTYPE events (data_loading.cpp:33-219); a serialised
                                 dvs_msgs/Event is 13 bytes {uint16 x, uint16 y, time ts, bool polarity},
                                 the in-memory struct the engine takes is the 16-byte padded one
+  sensor_msgs/CameraInfo     -> dict(width, height, distortion_model, D, K, R, P)
+
+parse_rosbag() is data_loading::parse_rosbag itself: the time window relative to the process-wide first stamp, the
+re-timing of events and poses, the stop-after-the-message rule and the final sort.
 
 The writer exists so that tests can round-trip synthetic streams; it emits one uncompressed chunk per
 call plus the index records rosbag tools expect.  bz2 / lz4 chunk compression is not supported.
@@ -128,6 +132,123 @@ def read_events(path, topic=None, t_min=None, t_max=None, sort=True):
     return ev
 
 
+# ---- data_loading::parse_rosbag ------------------------------------------------------------------------
+class TimeOrigin:
+    """The `static ros::Time initial_timestamp` of data_loading.cpp:30-31: the first stamp seen by the first
+    parse_rosbag call of a process becomes the origin of every later call (left and right bags share it)."""
+
+    def __init__(self):
+        self.stamp = None     # (sec, nsec)
+
+    def to_sec(self):
+        return self.stamp[0] + 1e-9 * self.stamp[1]
+
+
+DEFAULT_ORIGIN = TimeOrigin()
+
+
+def _time_from_sec(t):
+    """ros::Time(double): sec = floor(t), nsec = round((t - sec) * 1e9), normalised; negative times throw."""
+    if t < 0 or t >= 4294967296.0:
+        raise ValueError(f"ros::Time out of range: {t}")
+    sec = int(np.floor(t))
+    nsec = int(np.floor((t - sec) * 1e9 + 0.5))
+    if nsec >= 1_000_000_000:
+        sec, nsec = sec + 1, nsec - 1_000_000_000
+    return sec, nsec
+
+
+def parse_camera_info(p):
+    """sensor_msgs/CameraInfo payload -> dict(width, height, distortion_model, D, K, R, P)."""
+    _, o = _skip_std_header(p)
+    height, width, n = struct.unpack_from("<III", p, o)
+    o += 12
+    model = bytes(p[o:o + n]).decode()
+    o += n
+    (nd,) = struct.unpack_from("<I", p, o)
+    o += 4
+    D = np.frombuffer(p, "<f8", count=nd, offset=o).copy()
+    o += 8 * nd
+    K = np.frombuffer(p, "<f8", count=9, offset=o).reshape(3, 3).copy()
+    R = np.frombuffer(p, "<f8", count=9, offset=o + 72).reshape(3, 3).copy()
+    P = np.frombuffer(p, "<f8", count=12, offset=o + 144).reshape(3, 4).copy()
+    return dict(width=int(width), height=int(height), distortion_model=model, D=D, K=K, R=R, P=P)
+
+
+_POSE_TYPES = {"geometry_msgs/PoseStamped", "geometry_msgs/PoseWithCovarianceStamped"}
+
+
+def parse_rosbag(path, event_topic, camera_info_topic=None, pose_topic=None, tmin=0.0, tmax=float("inf"),
+                 events_offset=0.0, origin=None):
+    """data_loading::parse_rosbag (data_loading.cpp:33-219 with a pose topic, :221-303 without): events, control
+    poses and the last CameraInfo of one bag, restricted to [tmin, tmax] seconds after the process-wide first stamp
+    and re-timed relative to it (events additionally shifted by -events_offset).
+
+    Kept literally: messages are visited in bag-time order; an event / pose past tmax stops the loop only AFTER its
+    message has been consumed (so the last message may contribute stamps > tmax); empty EventArrays are skipped; the
+    events are sorted by timestamp at the end; poses come back sorted by their re-timed stamp (std::map), a later
+    pose with an equal stamp does not replace an earlier one (std::map::insert).
+    Returns (events EVENT_DTYPE, poses STAMPED_POSE_DTYPE, camera_info dict or None)."""
+    origin = DEFAULT_ORIGIN if origin is None else origin
+    topics = {t for t in (event_topic, camera_info_topic, pose_topic) if t}
+    msgs = sorted(read_messages(path, topics=topics), key=lambda m: m[2])      # rosbag::View: by receive time (stable)
+    ev_parts, poses, cam_info, go_on = [], {}, None, True
+    for topic, mtype, _, p in msgs:
+        if not go_on:
+            break
+        if topic == event_topic and mtype == "dvs_msgs/EventArray":
+            _, o = _skip_std_header(p)
+            _, _, n = struct.unpack_from("<III", p, o)
+            if n == 0:
+                continue
+            wire = np.frombuffer(p, _EV_WIRE, count=n, offset=o + 12)
+            if origin.stamp is None:
+                origin.stamp = (int(wire["sec"][0]), int(wire["nsec"][0]))
+            # (a - b).toSec() of two ros::Time values: the exact sec / nsec difference as a double
+            rel = (wire["sec"].astype(np.int64) - origin.stamp[0]).astype(np.float64) \
+                + 1e-9 * (wire["nsec"].astype(np.int64) - origin.stamp[1]).astype(np.float64)
+            if (rel > tmax).any():
+                go_on = False
+            keep = ~(rel < tmin)
+            if keep.any():
+                w = wire[keep]
+                t_new = (w["sec"].astype(np.float64) + 1e-9 * w["nsec"].astype(np.float64)) - origin.to_sec() - events_offset
+                if (t_new < 0).any():
+                    raise ValueError("parse_rosbag: a re-timed event stamp is negative (ros::Time would throw)")
+                sec = np.floor(t_new)
+                nsec = np.floor((t_new - sec) * 1e9 + 0.5)
+                carry = nsec >= 1e9
+                sec, nsec = sec + carry, nsec - carry * 1e9
+                e = np.zeros(w.shape[0], EVENT_DTYPE)
+                e["x"], e["y"], e["polarity"] = w["x"], w["y"], w["polarity"]
+                e["sec"], e["nsec"] = sec.astype(np.uint32), nsec.astype(np.uint32)
+                ev_parts.append(e)
+        elif topic == camera_info_topic and mtype == "sensor_msgs/CameraInfo":
+            cam_info = parse_camera_info(p)
+        elif topic == pose_topic and mtype in _POSE_TYPES:
+            stamp, o = _skip_std_header(p)
+            if origin.stamp is None:
+                origin.stamp = stamp
+            rel = (stamp[0] - origin.stamp[0]) + 1e-9 * (stamp[1] - origin.stamp[1])
+            if rel < tmin:
+                continue
+            if rel > tmax:
+                go_on = False
+            px, py, pz, qx, qy, qz, qw = struct.unpack_from("<7d", p, o)
+            key = _time_from_sec((stamp[0] + 1e-9 * stamp[1]) - origin.to_sec())
+            poses.setdefault(key, ((qw, qx, qy, qz), (px, py, pz)))
+        elif topic == pose_topic and mtype == "vicon/Subject":
+            raise NotImplementedError("vicon/Subject poses (EVIMO2) are not supported by rosbag_lite")
+    ev = np.concatenate(ev_parts) if ev_parts else np.zeros(0, EVENT_DTYPE)
+    key = ev["sec"].astype(np.uint64) * np.uint64(1_000_000_000) + ev["nsec"].astype(np.uint64)
+    ev = ev[np.argsort(key, kind="stable")]
+    arr = np.zeros(len(poses), STAMPED_POSE_DTYPE)
+    for i, k in enumerate(sorted(poses)):
+        arr["sec"][i], arr["nsec"][i] = k
+        arr["T"]["q"][i], arr["T"]["t"][i] = poses[k]
+    return ev, arr, cam_info
+
+
 # ---- writer (tests / synthetic data) ------------------------------------------------------------------
 def _hdr(**fields):
     b = b"".join(struct.pack("<I", len(k) + 1 + len(v)) + k.encode() + b"=" + v for k, v in fields.items())
@@ -142,17 +263,36 @@ def _std_header(seq, sec, nsec, frame_id=b""):
     return struct.pack("<IIII", seq, sec, nsec, len(frame_id)) + frame_id
 
 
+def serialize_camera_info(info, sec=0, nsec=0):
+    model = info["distortion_model"].encode()
+    D = np.asarray(info["D"], "<f8").reshape(-1)
+    return (_std_header(0, sec, nsec) + struct.pack("<III", info["height"], info["width"], len(model)) + model +
+            struct.pack("<I", len(D)) + D.tobytes() + np.asarray(info["K"], "<f8").tobytes() +
+            np.asarray(info["R"], "<f8").tobytes() + np.asarray(info["P"], "<f8").tobytes() +
+            struct.pack("<II", 0, 0) + struct.pack("<IIIIB", 0, 0, 0, 0, 0))
+
+
 def write_bag(path, poses=None, pose_topic="/pose", events=None, event_topic="/dvs/events", sensor=(640, 480),
-              events_per_message=5000):
-    """Writes one bag holding the given control poses (STAMPED_POSE_DTYPE) and / or events (EVENT_DTYPE)."""
+              events_per_message=5000, camera_info=None, camera_info_topic="/dvs/camera_info", pose_with_covariance=False):
+    """Writes one bag holding the given control poses (STAMPED_POSE_DTYPE), events (EVENT_DTYPE) and / or one
+    sensor_msgs/CameraInfo (a dict as parse_camera_info returns)."""
     conns, msgs = [], []   # msgs: (conn id, (sec, nsec), payload)
     if poses is not None:
         cid = len(conns)
-        conns.append((pose_topic, "geometry_msgs/PoseStamped", "d3812c3cbc69362b77dc0b19b345f8f5"))
+        if pose_with_covariance:
+            conns.append((pose_topic, "geometry_msgs/PoseWithCovarianceStamped", "953b798c0f514ff060a53a3498ce6246"))
+        else:
+            conns.append((pose_topic, "geometry_msgs/PoseStamped", "d3812c3cbc69362b77dc0b19b345f8f5"))
         for i, p in enumerate(np.asarray(poses, STAMPED_POSE_DTYPE)):
             q, t = p["T"]["q"], p["T"]["t"]
             msgs.append((cid, (int(p["sec"]), int(p["nsec"])), _std_header(i, int(p["sec"]), int(p["nsec"])) +
-                         struct.pack("<7d", t[0], t[1], t[2], q[1], q[2], q[3], q[0])))
+                         struct.pack("<7d", t[0], t[1], t[2], q[1], q[2], q[3], q[0]) +
+                         (struct.pack("<36d", *([0.0] * 36)) if pose_with_covariance else b"")))
+    if camera_info is not None:
+        cid = len(conns)
+        conns.append((camera_info_topic, "sensor_msgs/CameraInfo", "c9a58c1b0b154e0e6da7578cb991d214"))
+        first = min([m[1] for m in msgs], default=(0, 0))
+        msgs.append((cid, first, serialize_camera_info(camera_info, *first)))
     if events is not None:
         cid = len(conns)
         conns.append((event_topic, "dvs_msgs/EventArray", "5e8beee5a6c107e504c2e78903c224b8"))
