@@ -654,3 +654,41 @@ def process_2(ctx, cams, trajectories, events, dsi_shape, num_subintervals, T_rv
     mapper1.close()
     fused_sub.close()
     return dict(fused=fused, left=left, right=right, camera_time=camera_time)
+
+
+def process_2_sharded(ctx, cams, trajectories, events, dsi_shape, T_rv_w, stereo_fusion, temporal_fusion, rank, world):
+    """Alg. 2 with ONE sub-interval per GPU (BASELINE.json configs[3], the "AtHc" ordering): rank r builds the DSIs of
+    both cameras for sub-interval r of `world`, fuses them across cameras locally, and the fusion across time is the
+    only exchange — ONE ncclAllReduce(sum) of the camera-fused volume (of 1/(0.01 + x) for the harmonic temporal
+    mean), followed by the local finalisation (/world, or world/sum).  That is exactly the `fused` output of
+    process_2(num_subintervals=world) (process2.cpp:98-247) with the time loop spread over the ranks; float sums
+    differ by the allreduce order only.  Needs ctx.comm_init; every rank returns the same Grid3D.
+
+    NOTE: composed from calls that are each covered by the GPU suite (evaluateDSI, Grid3D ops, Grid3D.allreduce); the
+    composition itself has not been run on a multi-GPU box in round 1."""
+    if stereo_fusion not in _PAIR_METHOD:
+        raise ValueError("Improper fusion method selected")
+    if temporal_fusion not in (2, 4):
+        raise ValueError("process_2_sharded: temporal fusion 2 (harmonic) or 4 (arithmetic) — the other ids accumulate nothing")
+    ev = [np.ascontiguousarray(e, dtype=EVENT_DTYPE) for e in events]
+    mappers = [MapperEMVS(ctx, c, dsi_shape) for c in cams]
+    for m, e, tr in zip(mappers, ev, trajectories):
+        (lo, hi), = subinterval_slices(len(e), world)[rank]
+        if not m.evaluateDSI(e[lo:hi], tr, T_rv_w):
+            m.dsi_.resetGrid()
+    dimX, dimY, dimZ = mappers[0].dsi_.size_
+    fused_sub, fused = Grid3D(ctx, dimX, dimY, dimZ), Grid3D(ctx, dimX, dimY, dimZ)
+    fused_sub.copyFrom(mappers[0].dsi_)
+    getattr(fused_sub, _PAIR_METHOD[stereo_fusion])(mappers[1].dsi_)
+    if temporal_fusion == 2:
+        fused.addInverseOfTwoGrids(fused_sub)
+        fused.allreduce()
+        fused.computeHMfromSumOfInv(world)
+    else:
+        fused.addTwoGrids(fused_sub)
+        fused.allreduce()
+        fused.computeAMfromSum(world)
+    for m in mappers:
+        m.close()
+    fused_sub.close()
+    return fused
