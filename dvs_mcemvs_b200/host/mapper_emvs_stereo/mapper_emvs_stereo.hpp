@@ -194,6 +194,23 @@ class MapperEMVS {
     return true;
   }
 
+  // Streaming callers (main.cpp's full_seq loop): announce the arguments of a LATER evaluateDSI call on this mapper.
+  // The event upload starts and the host packet stage runs now, under whatever the device is computing; the later
+  // evaluateDSI with the same arguments only launches kernels.  `events` and `trajectory` must stay unchanged until then.
+  // (No counterpart in the reference: it is what hides PCIe behind the previous window's votes.)
+  void prefetchDSI(const emvs_event* events, size_t n_events, const TrajectoryType& trajectory,
+                   const geometry_utils::Transformation& T_rv_w)
+  {
+    emvs_host::check(emvs_mapper_prefetch_dsi(m_, events, n_events, trajectory.pods().data(), trajectory.pods().size(),
+                                              &T_rv_w.pod()),
+                     "prefetchDSI");
+  }
+  void prefetchDSI(const std::vector<emvs_event>& events, const TrajectoryType& trajectory,
+                   const geometry_utils::Transformation& T_rv_w)
+  {
+    prefetchDSI(events.data(), events.size(), trajectory, T_rv_w);
+  }
+
   // Hot part of getDepthMapFromDSI (method = -1): collapseMaxZSlice + convertDepthIndicesToValues.
   // depth_map = raw_depths_vec_[argmax] for EVERY pixel; the caller's mask / median / inpainting
   // (mapper_emvs_stereo.cpp:378-436) runs on these three maps.
