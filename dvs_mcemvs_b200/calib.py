@@ -12,6 +12,7 @@ against OpenCV, tests/test_rectify_lut.py) and 4x4 float64 matrices.
   kalibr_yaml_mvsec / kalibr_yaml_m3ed             get_camera_calib_yaml_mvsec / _m3ed  calib.cpp:141-228, 811-885
   esim_yaml(rig.yaml)                              get_camera_calib_yaml                calib.cpp:231-267
   basalt_json(calib.json[, mocap.json])            get_camera_calib_json (TUM-VIE)      calib.cpp:271-361
+  slider(), hkust(), evimo2(), esim()              the remaining hard-coded rigs        calib.cpp:591-806, 897-925
 
 Conventions kept literally: the rectification rotation is ignored (R = I: "work on unrectified images"); when the file
 has no projection matrix, P = cv::getOptimalNewCameraMatrix(K, D, size, alpha = 0); BOTH cameras get camera 0's P;
@@ -281,3 +282,88 @@ def basalt_json(camera_calib_path, mocap_calib_path=None):
             e = json.load(f)["value0"]["T_imu_marker"]
         hand_eye = np.linalg.inv(_pose4(e["qw"], e["qx"], e["qy"], e["qz"], e["px"], e["py"], e["pz"])) @ T_imu_cam[0]
     return StereoCalib(_camera(infos[0]), _camera(infos[1]), mat_1_0, hand_eye, infos)
+
+
+# ---- the remaining hard-coded rigs of calib.cpp ------------------------------------------------------------------
+def _fixed(width, height, K, D, R, P):
+    return dict(width=width, height=height, K=np.asarray(K, np.float64).reshape(3, 3), D=np.asarray(D, np.float64),
+                R=np.asarray(R, np.float64).reshape(3, 3), P=np.asarray(P, np.float64).reshape(3, 4), distortion_model="plumb_bob")
+
+
+def _translation(x, y=0.0, z=0.0):
+    m = np.eye(4)
+    m[:3, 3] = [x, y, z]
+    return m
+
+
+def esim():
+    """get_camera_calib_ESIM (calib.cpp:897-925): 240x180, f = 200, no distortion, 0.2 m baseline."""
+    info = _fixed(240, 180, [200, 0, 120, 0, 200, 90, 0, 0, 1], [0.0] * 5, np.eye(3), [200, 0, 120, 0, 0, 200, 90, 0, 0, 0, 1, 0])
+    return StereoCalib(_camera(info), _camera(info), _translation(-0.2), np.eye(4), [info, dict(info)])
+
+
+def slider():
+    """get_camera_calib_slider (calib.cpp:591-631): the rpg stereo DAVIS slider, WITH rectification rotations, one
+    projection matrix for both cameras, 0.15 m baseline."""
+    P = [193.4488673170594, 0, 137.1049880981445, 0, 0, 193.4488673170594, 108.951057434082, 0, 0, 0, 1, 0]
+    i0 = _fixed(240, 180, [198.9035679113487, 0, 139.8751842835105, 0, 198.8472302496314, 104.0170363461823, 0, 0, 1],
+                [-0.3693817071651257, 0.1677750957297015, 0.0007676172676998043, -0.001200264930281811, 0],
+                [0.9997156212398773, 0.02379292338064179, 0.001604196362382244,
+                 -0.02378757584963585, 0.9997116745775861, -0.003273980524687744,
+                 -0.001681631399562056, 0.003234889531517614, 0.9999933537806914], P)
+    i1 = _fixed(240, 180, [198.1315372343827, 0, 132.4194623418875, 0, 198.0677328525099, 111.1773834719834, 0, 0, 1],
+                [-0.3425648318682812, 0.1238467273033616, 0.0004063467878750188, 0.0004690582572504908, 0],
+                [0.9999365173339012, 0.007076042854404519, 0.008768746756027635,
+                 -0.007104545173989656, 0.999969566560146, 0.003223568113795293,
+                 -0.008745669786783357, -0.003285661430544528, 0.9999563578921555], P)
+    return StereoCalib(_camera(i0), _camera(i1), _translation(-0.15), np.eye(4), [i0, i1])
+
+
+def hkust():
+    """get_camera_calib_hkust (calib.cpp:635-674).  Camera 1's K carries a non-standard third row in the reference;
+    only fx, fy, cx, cy of K enter the rectification (cv::undistortPoints), so it is kept as written."""
+    P = [189.705, 0, 165.382, 0, 0, 189.705, 121.295, 0, 0, 0, 1, 0]
+    i0 = _fixed(346, 260, [263.796, 0, 176.994, 0, 263.738, 124.373, 0, 0, 1],
+                [-0.386589, 0.157241, 0.000322143, 6.13759e-06], np.eye(3), P)
+    i1 = _fixed(346, 260, [263.485, 0, 162.942, 0, 263.276, 118.029, -0.0151344, 0.00133093, 0.999885],
+                [-0.383425, 0.152823, -0.000257745, 0.000268432], np.eye(3), P)
+    mat_1_0 = np.array([[9.99990798e-01, -6.32492385e-04, -4.24307214e-03, -7.30597639e-02],
+                        [6.44736387e-04, 9.99995631e-01, 2.88489843e-03, -1.23275257e-03],
+                        [4.24122892e-03, -2.88760755e-03, 9.99986837e-01, -1.10420407e-03], [0, 0, 0, 1.0]])
+    return StereoCalib(_camera(i0), _camera(i1), mat_1_0, np.eye(4), [i0, i1])
+
+
+def _rpy_pose(x, y, z, roll, pitch, yaw):
+    """tf::Quaternion::setRPY + tf::Transform: R = Rz(yaw) Ry(pitch) Rx(roll)."""
+    cr, sr, cp, sp, cy, sy = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    m = np.eye(4)
+    m[:3, :3] = [[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                 [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                 [-sp, cp * sr, cp * cr]]
+    m[:3, 3] = [x, y, z]
+    return m
+
+
+class TrinocularCalib(StereoCalib):
+    """EVIMO2: three event cameras (cam2, mat_2_0 beside the stereo fields)."""
+
+    def __init__(self, cam0, cam1, cam2, mat_1_0, mat_2_0, mat_hand_eye, info):
+        super().__init__(cam0, cam1, mat_1_0, mat_hand_eye, info)
+        self.cam2, self.mat_2_0 = cam2, mat_2_0
+
+
+def evimo2():
+    """get_camera_calib_evimo2 (calib.cpp:678-806): three 640x480 cameras sharing camera 0's optimal projection matrix,
+    extrinsics given as x y z roll pitch yaw wrt the rig base."""
+    Ks = [(519.638, 519.384, 321.661, 240.727), (558.417, 557.475, 324.905, 225.3), (556.184, 555.632, 326.875, 202.887)]
+    Ds = [(0.108306, -0.154485, 0.00103538, -0.000401824), (-0.115993, 0.204851, -0.00217161, 0.000676025),
+          (-0.110194, 0.205049, 0.00206719, -0.00040706)]
+    infos = [_info(640, 480, *k, "plumb_bob", d) for k, d in zip(Ks, Ds)]
+    infos[0]["P"] = optimal_projection(infos[0]["K"], infos[0]["D"], 640, 480)
+    infos[1]["P"] = infos[2]["P"] = infos[0]["P"]
+    ext = [(0.135419, -0.0214639, -0.0715952, -0.00748326, 0.0496968, -1.79144),
+           (0.118804, 0.0850843, -0.0194297, 0.018838, 0.00459314, -0.195708),
+           (0.0754507, -0.119035, -0.0336873, -0.0122178, -0.00473387, 2.93835)]
+    T_B = [_rpy_pose(*e) for e in ext]
+    return TrinocularCalib(_camera(infos[0]), _camera(infos[1]), _camera(infos[2]), np.linalg.inv(T_B[1]) @ T_B[0],
+                           np.linalg.inv(T_B[2]) @ T_B[0], T_B[0], infos)

@@ -148,3 +148,41 @@ def test_mvsec_esim_and_basalt_loaders(tmp_path):
     got = np.array([b.cam1.lut[int(y) * 1280 + int(x)] for x, y in pts.reshape(-1, 2)])
     np.testing.assert_allclose(got, want, atol=2e-3)
     assert np.array_equal(calib.basalt_json(str(j)).mat_hand_eye[:3, 3], [0.05, 0.0, 0.0])
+
+
+def test_hard_coded_rigs():
+    e = calib.esim()
+    assert (e.cam0.width, e.cam0.height, e.cam0.fx, e.cam0.cx, e.cam0.cy) == (240, 180, 200.0, 120.0, 90.0)
+    assert e.mat_1_0[0, 3] == -0.2 and e.cam1.lut[0].tolist() == [0.0, 0.0]
+    # the engine's synthetic ESIM rig (BASELINE configs[0]) is this calibration
+    rig = synth.rig_esim()
+    assert (rig.cams[0].fx, rig.cams[0].cx, rig.cams[0].cy) == (e.cam0.fx, e.cam0.cx, e.cam0.cy)
+
+    s = calib.slider()                                           # rectification rotations R != I enter the LUT
+    assert s.mat_1_0[0, 3] == -0.15 and (s.cam0.fx, s.cam0.cx) == (s.cam1.fx, s.cam1.cx) == (193.4488673170594, 137.1049880981445)
+    for cam, info in zip((s.cam0, s.cam1), s.info):
+        pts = np.array([[[0.0, 0.0]], [[239.0, 179.0]], [[120.0, 90.0]], [[33.0, 150.0]]], np.float64)
+        want = cv2.undistortPoints(pts, info["K"], info["D"], R=info["R"], P=info["P"]).reshape(-1, 2)
+        got = np.array([cam.lut[int(y) * 240 + int(x)] for x, y in pts.reshape(-1, 2)])
+        np.testing.assert_allclose(got, want.astype(np.float32), atol=2e-4)
+
+    h = calib.hkust()
+    assert (h.cam1.width, h.cam1.height, h.cam1.fx) == (346, 260, 189.705) and h.mat_1_0[0, 3] == pytest.approx(-0.0730597639)
+    info = h.info[1]
+    Kstd = info["K"].copy()
+    Kstd[2] = [0, 0, 1]                                          # cv::undistortPoints ignores K's third row
+    pts = np.array([[[10.0, 10.0]], [[300.0, 200.0]]], np.float64)
+    want = cv2.undistortPoints(pts, Kstd, info["D"], R=np.eye(3), P=info["P"]).reshape(-1, 2)
+    got = np.array([h.cam1.lut[int(y) * 346 + int(x)] for x, y in pts.reshape(-1, 2)])
+    np.testing.assert_allclose(got, want.astype(np.float32), atol=2e-4)
+
+    v = calib.evimo2()
+    assert (v.cam2.fx, v.cam2.cx) == (v.cam0.fx, v.cam0.cx) and v.cam2.lut.shape == (640 * 480, 2)
+    for m in (v.mat_1_0, v.mat_2_0, v.mat_hand_eye):
+        np.testing.assert_allclose(m[:3, :3] @ m[:3, :3].T, np.eye(3), atol=1e-12)
+        assert np.linalg.det(m[:3, :3]) == pytest.approx(1.0)
+    # T_B_0 = Rz(yaw) Ry(pitch) Rx(roll): yaw -1.79 rad maps the base x axis mostly onto -y
+    assert v.mat_hand_eye[:3, 3].tolist() == [0.135419, -0.0214639, -0.0715952]
+    assert v.mat_hand_eye[1, 0] == pytest.approx(np.sin(-1.79144) * np.cos(0.0496968))
+    # cameras 0 and 1 are ~11 cm apart, cameras 0 and 2 ~11.8 cm
+    assert 0.10 < np.linalg.norm(v.mat_1_0[:3, 3]) < 0.12 and 0.10 < np.linalg.norm(v.mat_2_0[:3, 3]) < 0.13
