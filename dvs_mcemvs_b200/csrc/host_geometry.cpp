@@ -390,7 +390,13 @@ size_t host_packetize_range(const emvs_event* ev, size_t n_ev, const emvs_stampe
   S.Kinv_virtual = inverse(pinhole_K(virt[0], virt[1], virt[2], virt[3]));
   S.T_rv_w = load(T_rv_w_pod);
   S.z0 = z0;
-  constexpr size_t kStreak = 4, kMinBatch = 512;
+  constexpr size_t kStreak = 4;
+  // below this many remaining packets the thread start-up costs more than it saves (tests lower it to exercise the
+  // speculative path on short lists)
+  static const size_t kMinBatch = [] {
+    const char* e = std::getenv("EMVS_PACKET_MIN_BATCH");
+    return (size_t)std::max(1, e ? std::atoi(e) : 512);
+  }();
   size_t produced = 0, streak = 0;
   size_t cur = *cur_inout;
   auto fits = [&](size_t c) { return c + EMVS_PACKET_SIZE < n_ev && c + EMVS_PACKET_SIZE <= event_limit; };
