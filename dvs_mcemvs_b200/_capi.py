@@ -44,6 +44,11 @@ class Camera(C.Structure):
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
 
 
+class EventsSoA(C.Structure):
+    """emvs_events_soa: separate x / y (uint16) and t_ns (int64) arrays of one event list."""
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("t_ns", C.c_void_p), ("n", C.c_size_t)]
+
+
 class DepthMapOptions(C.Structure):
     _fields_ = [("adaptive_threshold_kernel_size", C.c_int32), ("adaptive_threshold_c", C.c_double),
                 ("max_confidence", C.c_double), ("median_filter_size", C.c_int32)]
@@ -65,7 +70,13 @@ _PROTOTYPES = {
     "emvs_context_set_slab": (C.c_int, [_vp, C.c_uint32]),
     "emvs_context_set_upload_split": (C.c_int, [_vp, C.c_uint32, C.c_uint64]),
     "emvs_context_prefetch_events": (C.c_int, [_vp, _vp, _sz]),
+    "emvs_context_prefetch_pending": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "emvs_context_prefetch_cancel": (C.c_int, [_vp]),
     "emvs_mapper_prefetch_dsi": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "emvs_mapper_prefetch_dsi_soa": (C.c_int, [_vp, C.POINTER(EventsSoA), _vp, _sz, _vp]),
+    "emvs_mapper_evaluate_dsi_soa": (C.c_int, [_vp, C.POINTER(EventsSoA), _vp, _sz, _vp, C.c_int]),
+    "emvs_packetize_soa": (C.c_int, [C.POINTER(EventsSoA), _vp, _sz, _vp, C.POINTER(Camera), _vp, C.c_float, _vp, _sz,
+                                     C.POINTER(_sz)]),
     "emvs_selftest_division": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "emvs_context_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "emvs_context_profile_vote": (C.c_int, [_vp, C.c_int]),

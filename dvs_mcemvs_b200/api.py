@@ -72,6 +72,40 @@ class CameraModel:
         return cls(width, height, P[0], P[5], P[2], P[6], lut=lut)
 
 
+class EventsSoA:
+    """Structure-of-arrays event list (emvs_events_soa): x, y uint16 and t_ns int64 (ros::Time::toNSec()), the
+    layout of the DSEC / TUM-VIE HDF5 event files.  Only x and y travel to the GPU (4 bytes per event); the
+    packet stage reads one timestamp per 1024 events on the host.  The arrays are kept alive by this object."""
+
+    def __init__(self, x, y, t_ns):
+        self.x = np.ascontiguousarray(x, dtype=np.uint16)
+        self.y = np.ascontiguousarray(y, dtype=np.uint16)
+        self.t_ns = np.ascontiguousarray(t_ns, dtype=np.int64)
+        if not (self.x.shape == self.y.shape == self.t_ns.shape and self.x.ndim == 1):
+            raise ValueError("x, y, t_ns must be 1-D arrays of equal length")
+
+    @classmethod
+    def from_events(cls, events, pinned=False):
+        """From a dvs_msgs::Event-layout array (EVENT_DTYPE)."""
+        t = events["sec"].astype(np.int64) * 1_000_000_000 + events["nsec"].astype(np.int64)
+        if not pinned:
+            return cls(events["x"], events["y"], t)
+        out = cls.__new__(cls)
+        out.x, out.y, out.t_ns = (pinned_empty(len(events), d) for d in (np.uint16, np.uint16, np.int64))
+        out.x[...], out.y[...], out.t_ns[...] = events["x"], events["y"], t
+        return out
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    @property
+    def nbytes_device(self):
+        return self.x.nbytes + self.y.nbytes
+
+    def c_struct(self):
+        return capi.EventsSoA(self.x.ctypes.data, self.y.ctypes.data, self.t_ns.ctypes.data, self.x.shape[0])
+
+
 def make_pose(q=(1.0, 0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0)):
     p = np.zeros((), dtype=POSE_DTYPE)
     p["q"] = q
@@ -124,11 +158,13 @@ class Context:
         check(_lib().emvs_context_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        self._prefetch_ref = None   # the arrays of the pending prefetch: they must outlive it (the engine matches by address)
 
     def close(self):
         if getattr(self, "_h", None):
             _lib().emvs_context_destroy(self._h)
             self._h = None
+            self._prefetch_ref = None
 
     __del__ = close
 
@@ -148,6 +184,20 @@ class Context:
         if events.dtype != EVENT_DTYPE or not events.flags["C_CONTIGUOUS"]:
             raise ValueError("prefetch_events needs a contiguous EVENT_DTYPE array (the later call must see the same buffer)")
         check(_lib().emvs_context_prefetch_events(self._h, ptr(events), events.shape[0]))
+        self._prefetch_ref = events
+
+    def prefetch_pending(self):
+        """Generation number of the pending prefetch, 0 when none is pending."""
+        g = C.c_uint64(0)
+        check(_lib().emvs_context_prefetch_pending(self._h, C.byref(g)))
+        if not g.value:
+            self._prefetch_ref = None
+        return g.value
+
+    def prefetch_cancel(self):
+        """Withdraw the pending prefetch (waits for its copies); its arrays may be freed or rewritten afterwards."""
+        check(_lib().emvs_context_prefetch_cancel(self._h))
+        self._prefetch_ref = None
 
     def selftest_division(self, n_pairs=1 << 28, seed=1):
         """Mismatches between the vote kernel's prepared division and __fdiv_rn over ~n_pairs operand pairs."""
@@ -466,16 +516,25 @@ class MapperEMVS:
     __del__ = close
 
     def packetize(self, events, trajectory, T_rv_w):
-        """Packet stage of evaluateDSI (mapper_emvs_stereo.cpp:86-126) -> packets, or None if < 1024 events."""
-        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
-        n = events.shape[0]
-        out = np.zeros(n // capi.PACKET_SIZE + 1, dtype=PACKET_DTYPE)
+        """Packet stage of evaluateDSI (mapper_emvs_stereo.cpp:86-126) -> packets, or None if < 1024 events.
+        `events`: EVENT_DTYPE array or EventsSoA."""
         n_pk = C.c_size_t(0)
         cs = self.cam.c_struct()
-        rc = _lib().emvs_packetize(ptr(events), n, ptr(trajectory.poses), trajectory.poses.shape[0],
-                                   ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE)), C.byref(cs),
-                                   ptr(self.virtual_cam_), float(self.raw_depths_vec_[0]), ptr(out), out.shape[0],
-                                   C.byref(n_pk))
+        T = ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE))
+        if isinstance(events, EventsSoA):
+            n = len(events)
+            out = np.zeros(n // capi.PACKET_SIZE + 1, dtype=PACKET_DTYPE)
+            es = events.c_struct()
+            rc = _lib().emvs_packetize_soa(C.byref(es), ptr(trajectory.poses), trajectory.poses.shape[0], T, C.byref(cs),
+                                           ptr(self.virtual_cam_), float(self.raw_depths_vec_[0]), ptr(out), out.shape[0],
+                                           C.byref(n_pk))
+        else:
+            events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+            n = events.shape[0]
+            out = np.zeros(n // capi.PACKET_SIZE + 1, dtype=PACKET_DTYPE)
+            rc = _lib().emvs_packetize(ptr(events), n, ptr(trajectory.poses), trajectory.poses.shape[0], T, C.byref(cs),
+                                       ptr(self.virtual_cam_), float(self.raw_depths_vec_[0]), ptr(out), out.shape[0],
+                                       C.byref(n_pk))
         if rc == capi.EMVS_ERR_TOO_FEW:
             return None
         check(rc)
@@ -499,20 +558,32 @@ class MapperEMVS:
         """Streaming callers: start the upload AND the host packet stage of a LATER evaluateDSI(events, trajectory,
         T_rv_w) on this mapper now, under the current device work; that call then only launches kernels.  `events`
         must be the same contiguous EVENT_DTYPE array object (ideally pinned), `trajectory` the same object."""
-        if events.dtype != EVENT_DTYPE or not events.flags["C_CONTIGUOUS"]:
-            raise ValueError("prefetch needs a contiguous EVENT_DTYPE array (the later call must see the same buffer)")
-        check(_lib().emvs_mapper_prefetch_dsi(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
-                                              trajectory.poses.shape[0],
-                                              ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE))))
+        T = ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE))
+        if isinstance(events, EventsSoA):
+            es = events.c_struct()
+            check(_lib().emvs_mapper_prefetch_dsi_soa(self._h, C.byref(es), ptr(trajectory.poses), trajectory.poses.shape[0], T))
+        else:
+            if events.dtype != EVENT_DTYPE or not events.flags["C_CONTIGUOUS"]:
+                raise ValueError("prefetch needs a contiguous EVENT_DTYPE array (the later call must see the same buffer)")
+            check(_lib().emvs_mapper_prefetch_dsi(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
+                                                  trajectory.poses.shape[0], T))
+        # the engine recognises the later call by the arrays' addresses: keep them (and the poses) alive until then
+        self.ctx._prefetch_ref = (events, trajectory)
 
     def evaluateDSI(self, events, trajectory, T_rv_w, allreduce=False, peer_reduce=False):
         """bool evaluateDSI(events, trajectory, T_rv_w) — mapper_emvs_stereo.cpp:67-148.
+        `events`: EVENT_DTYPE array (std::vector<dvs_msgs::Event>) or EventsSoA.
         allreduce / peer_reduce: the events are this rank's shard of a multi-GPU build."""
-        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
-        rc = _lib().emvs_mapper_evaluate_dsi_flags(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
-                                                   trajectory.poses.shape[0],
-                                                   ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE)),
-                                                   self._flags(False, allreduce, peer_reduce))
+        T = ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE))
+        flags = self._flags(False, allreduce, peer_reduce)
+        if isinstance(events, EventsSoA):
+            es = events.c_struct()
+            rc = _lib().emvs_mapper_evaluate_dsi_soa(self._h, C.byref(es), ptr(trajectory.poses), trajectory.poses.shape[0], T, flags)
+        else:
+            events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+            rc = _lib().emvs_mapper_evaluate_dsi_flags(self._h, ptr(events), events.shape[0], ptr(trajectory.poses),
+                                                       trajectory.poses.shape[0], T, flags)
+        self.ctx._prefetch_ref = None   # consumed or dropped by this call (emvs_b200.h: prefetch lifetime rule)
         if rc == capi.EMVS_ERR_TOO_FEW:
             return False
         check(rc)
@@ -530,6 +601,7 @@ class MapperEMVS:
         packets = np.ascontiguousarray(packets, dtype=PACKET_DTYPE)
         check(_lib().emvs_mapper_build(self._h, ptr(events), events.shape[0], ptr(packets), packets.shape[0],
                                        self._flags(accumulate, allreduce, peer_reduce)))
+        self.ctx._prefetch_ref = None
 
     def build_device(self, d_events, n_events, d_packets, n_packets, accumulate=False, allreduce=False, peer_reduce=False):
         """Same with device pointers (ints); asynchronous on the context's stream."""

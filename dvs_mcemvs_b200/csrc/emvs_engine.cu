@@ -78,10 +78,12 @@ struct emvs_context {
   unsigned upload_next = 0;            // staging buffer the next upload goes to
   int cur_events = 0;                  // staging buffer the current / last host-buffer build reads
   struct {                             // emvs_context_prefetch_events: a list already on its way to d_events[buf]
-    const emvs_event* host = nullptr;
+    const void* host = nullptr;        // the caller's event array (AoS) or x array (SoA): the key the later call is matched by
+    bool soa = false;
     size_t n = 0;
     int buf = 0;
     bool valid = false;
+    uint64_t generation = 0;
     // emvs_mapper_prefetch_dsi: its packet stage has run too and the packets are on their way to d_packets[par]
     bool has_packets = false;
     size_t n_pk = 0;
@@ -106,6 +108,12 @@ struct emvs_context {
   bool consumed_recorded[2] = {false, false};
   bool mark_consumed = false;          // build_on_device records ev_consumed after the event stage
   float2* d_xy0 = nullptr;   size_t xy0_cap = 0;
+  // k_vote_tma: one work counter per vote launch of a build (packets are handed out dynamically), zeroed when the
+  // build is issued; the persistent grid leaves one 256-thread slot per SM to the merge / exchange kernels
+  unsigned int* d_work = nullptr;
+  uint32_t vote_ctas_per_sm = 7;
+  bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
+  uint64_t prefetch_generation = 0;    // bumped by every prefetch; emvs_context_prefetch_pending reports the pending one
   void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
   void* d_fc_part = nullptr; size_t fc_part_cap = 0;  // per-chunk (max, index) of the Z-split sweep
   double* d_partial = nullptr;                        // 1024 partial sums + 1 result
@@ -199,6 +207,12 @@ int grow(void** p, size_t* cap, size_t need)
 
 inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+int env_int(const char* name, int dflt)
+{
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 // Planes voted per pass over the event list (the slab) and planes whose quads are interleaved in the scratch (the
 // plane group G of k_vote_grouped).  Measured on B200 (126 MB L2) at 640x480, profiles/r1_vote_group.md:
 //   * G = 8 with the events staged in shared memory and the grouped merge is the fastest (1235 Mevents/s against
@@ -285,17 +299,44 @@ int peer_reduce_slab(emvs_context* ctx, emvs_exchange* ex, int cam, uint32_t sla
   CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->slab_events[slab_idx], 0));
   const uint32_t p_lo = ex->row_lo * ex->dimX, p_hi = ex->row_hi * ex->dimX, band = p_hi - p_lo;
   if (band) {
-    const dim3 grid((band + 255) / 256, nk);
     float* out = ex->band_buf + ((size_t)cam * ex->dimZ + k0) * band;
-    k_peer_reduce_band<<<grid, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch, 40000000000LL,
-                                                           ex->flags + 16, p_lo, p_hi, ex->dimX * ex->dimY, k0, nk, out);
+    // EMVS_PEER_REDUCE_CTAS: size of the persistent reduce grid (0: one thread per voxel, thousands of CTAs)
+    static const int reduce_ctas = env_int("EMVS_PEER_REDUCE_CTAS", 64);
+    const uint32_t n_pix = ex->dimX * ex->dimY;
+    if (reduce_ctas > 0 && p_lo % 4 == 0 && band % 4 == 0 && n_pix % 4 == 0 && (((size_t)k0 * band) % 4) == 0) {
+      k_peer_reduce_band_v4<<<(unsigned)reduce_ctas, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch,
+                                                                                 40000000000LL, ex->flags + 16, p_lo, p_hi, n_pix,
+                                                                                 k0, nk, out);
+    } else {
+      const dim3 grid((band + 255) / 256, nk);
+      k_peer_reduce_band<<<grid, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch, 40000000000LL,
+                                                             ex->flags + 16, p_lo, p_hi, n_pix, k0, nk, out);
+    }
   }
   ctx->launches += 2;
   return EMVS_OK;
 }
 
+// Device-resident event list: the caller's 16-byte dvs_msgs::Event structs, or (emvs_events_soa) separate uint16
+// x / y arrays.
+struct EventSrc {
+  const emvs_event* aos = nullptr;
+  const uint16_t* x = nullptr;
+  const uint16_t* y = nullptr;
+};
+
+constexpr uint32_t kMaxWorkCounters = 4096;    // vote launches (slabs) per build
+
+// gentle re-zeroing of a merged scratch buffer: 256-thread CTAs that fit beside the persistent vote grid
+__global__ void __launch_bounds__(256) k_zero_f4(float4* __restrict__ p, size_t n)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = z;
+}
+
 // Device part of evaluateDSI: event stage, (reset), slab loop of {vote, merge, re-zero[, allreduce | peer reduce]}.
-int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, const emvs_packet* d_pk,
+int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const emvs_packet* d_pk,
                     size_t n_packets, int flags)
 {
   emvs_context* ctx = m->ctx;
@@ -362,11 +403,25 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
     const int rc = ensure_quad(ctx, b, slab_bytes);
     if (rc) return rc;
   }
+  // the vote kernels index a plane group with 32 bits
+  REQUIRE((uint64_t)QW * QH * 4 * G < (1ull << 32), EMVS_ERR_INVALID, "build: plane too large for the 32-bit quad index");
+  const uint32_t n_slabs = (dimZ + slab - 1) / slab;
+  const bool use_tma = ctx->vote_tma && G > 1;
+  if (use_tma) {
+    REQUIRE(n_slabs <= kMaxWorkCounters, EMVS_ERR_INVALID, "build: too many slabs (raise the slab size)");
+    REQUIRE(n_packets < (1ull << 31), EMVS_ERR_INVALID, "build: too many packets for one build");
+    if (!ctx->d_work) CUDA_TRY(cudaMalloc((void**)&ctx->d_work, sizeof(unsigned int) * kMaxWorkCounters));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int) * n_slabs, st));
+  }
 
   {
     const unsigned blocks = (unsigned)((n_voted + 255) / 256);
-    k_warp_events<<<blocks, 256, 0, st>>>(d_ev, d_pk, m->d_lut, m->cam.width, m->cam.height, ctx->d_xy0,
-                                          (unsigned long long)n_voted);
+    if (d_ev.aos)
+      k_warp_events<<<blocks, 256, 0, st>>>(d_ev.aos, d_pk, m->d_lut, m->cam.width, m->cam.height, ctx->d_xy0,
+                                            (unsigned long long)n_voted);
+    else
+      k_warp_events_soa<<<blocks, 256, 0, st>>>(d_ev.x, d_ev.y, d_pk, m->d_lut, m->cam.width, m->cam.height, ctx->d_xy0,
+                                                (unsigned long long)n_voted);
     ctx->launches++;
     if (ctx->mark_consumed) {
       CUDA_TRY(cudaEventRecord(ctx->ev_consumed[ctx->cur_events], st));
@@ -406,6 +461,24 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
     }
     const size_t smem_g = smem + (EMVS_PACKET_SIZE + nk) * sizeof(float2);   // + the packet's warped events + prepared reciprocals
     static const bool fastdiv = [] { const char* e = getenv("EMVS_VOTE_FASTDIV"); return e ? atoi(e) != 0 : false; }();
+    if (use_tma) {
+      // persistent grid: vote_ctas_per_sm CTAs per SM take packets from the slab's work counter; their event tiles
+      // arrive by cp.async.bulk (TMA) into two shared-memory stages
+      const unsigned grid = (unsigned)std::min<size_t>(n_packets, (size_t)ctx->sm_count * ctx->vote_ctas_per_sm);
+      const size_t smem_t = vote_tma_smem_bytes(nk);
+      unsigned int* wc = ctx->d_work + k0 / slab;
+#define LAUNCH_VOTE_T(GG)                                                                                                 \
+  k_vote_tma<GG><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_packets, P, ctx->quad[b], \
+                                                     m->d_counts, wc)
+      switch (G) {
+        case 2: LAUNCH_VOTE_T(2); break;
+        case 4: LAUNCH_VOTE_T(4); break;
+        case 8: LAUNCH_VOTE_T(8); break;
+        case 16: LAUNCH_VOTE_T(16); break;
+        default: LAUNCH_VOTE_T(32); break;
+      }
+#undef LAUNCH_VOTE_T
+    } else {
 #define LAUNCH_VOTE_GF(GG, FF)                                                                                         \
   k_vote_grouped<GG, FF><<<(unsigned)n_packets, kVoteThreads, smem_g, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], \
                                                                             m->d_counts)
@@ -414,17 +487,18 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
     if (fastdiv) LAUNCH_VOTE_GF(GG, true); \
     else LAUNCH_VOTE_GF(GG, false);        \
   } while (0)
-    switch (G) {
-      case 2: LAUNCH_VOTE_G(2); break;
-      case 4: LAUNCH_VOTE_G(4); break;
-      case 8: LAUNCH_VOTE_G(8); break;
-      case 16: LAUNCH_VOTE_G(16); break;
-      case 32: LAUNCH_VOTE_G(32); break;
-      default:
-        k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], m->d_counts);
-    }
+      switch (G) {
+        case 2: LAUNCH_VOTE_G(2); break;
+        case 4: LAUNCH_VOTE_G(4); break;
+        case 8: LAUNCH_VOTE_G(8); break;
+        case 16: LAUNCH_VOTE_G(16); break;
+        case 32: LAUNCH_VOTE_G(32); break;
+        default:
+          k_vote<<<(unsigned)n_packets, kVoteThreads, smem, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], m->d_counts);
+      }
 #undef LAUNCH_VOTE_G
 #undef LAUNCH_VOTE_GF
+    }
     ctx->launches++;
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
     if (overlap) {
@@ -432,7 +506,10 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
       CUDA_TRY(cudaStreamWaitEvent(ms, ctx->ev_vote[b], 0));
     }
     static const bool merge_grouped = [] { const char* e = getenv("EMVS_MERGE_GROUPED"); return e ? atoi(e) != 0 : true; }();
-    if (G > 1 && merge_grouped) {
+    // timing experiments only (profiles/r2_interference.md): the DSI is WRONG with either of them set
+    static const bool dbg_skip_merge = env_int("EMVS_DEBUG_SKIP_MERGE", 0) != 0, dbg_skip_zero = env_int("EMVS_DEBUG_SKIP_ZERO", 0) != 0;
+    if (dbg_skip_merge) {
+    } else if (G > 1 && merge_grouped) {
       const dim3 mg(ceil_div(QW, 256 / G), QH, ceil_div(nk, G));
       float* dst = g->d + (size_t)k0 * dimX * dimY;
 #define LAUNCH_MERGE_G(GG) k_merge_quads_grouped<GG><<<mg, 256, 0, ms>>>(ctx->quad[b], dst, dimX, dimY, QW, QH, nk, accumulate ? 1 : 0)
@@ -450,7 +527,19 @@ int build_on_device(emvs_mapper* m, const emvs_event* d_ev, size_t n_events, con
                                        accumulate ? 1 : 0, (int)G);
     }
     ctx->launches++;
-    CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, (size_t)round_up_g(nk) * QW * QH * 4 * sizeof(float4), ms));
+    {
+      // re-zero the merged buffer.  Beside the persistent vote grid only 256-thread CTAs find a slot, and a capped
+      // grid spreads the 79 MB of stores over the vote launch instead of bursting (EMVS_ZERO_CTAS=0: cudaMemsetAsync)
+      static const int zero_ctas = env_int("EMVS_ZERO_CTAS", 296);
+      const size_t n_f4 = (size_t)round_up_g(nk) * QW * QH * 4;
+      if (dbg_skip_zero) {
+      } else if (zero_ctas > 0) {
+        k_zero_f4<<<(unsigned)zero_ctas, 256, 0, ms>>>(ctx->quad[b], n_f4);
+        ctx->launches++;
+      } else {
+        CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, n_f4 * sizeof(float4), ms));
+      }
+    }
     if (overlap) {
       CUDA_TRY(cudaEventRecord(ctx->ev_merge[b], ms));
       ctx->merge_pending[b] = true;
@@ -520,9 +609,17 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
     per_chunk = (dimZ + n_chunks - 1) / n_chunks;
   }
   const uint32_t used_chunks = n_chunks > 1 ? (dimZ + per_chunk - 1) / per_chunk : 1;
+  // EMVS_FC_V4=1: four pixels per thread (16-byte loads); needs 16-byte aligned planes
+  static const bool fc_v4 = env_int("EMVS_FC_V4", 0) != 0;
+  const bool v4 = fc_v4 && n_chunks > 1 && n_pix % 4 == 0;
+  const unsigned blocks4 = (n_pix / 4 + 127) / 128;
 #define LAUNCH_M(M, N)                                                                                                     \
   do {                                                                                                                     \
-    if (n_chunks > 1) {                                                                                                    \
+    if (v4) {                                                                                                              \
+      k_fuse_collapse_zsplit_v4<M, N><<<dim3(blocks4, used_chunks), 128, 0, st>>>(A, n_pix, dimZ, per_chunk, fused, part_best, part_k); \
+      k_fc_combine<<<(n_pix + 255) / 256, 256, 0, st>>>(part_best, part_k, used_chunks, n_pix, d_depths, conf, idx, idx_bytes, depth); \
+      ctx->launches++;                                                                                                     \
+    } else if (n_chunks > 1) {                                                                                             \
       k_fuse_collapse_zsplit<M, N><<<dim3(blocks, used_chunks), 128, 0, st>>>(A, n_pix, dimZ, per_chunk, fused, part_best, part_k); \
       k_fc_combine<<<(n_pix + 255) / 256, 256, 0, st>>>(part_best, part_k, used_chunks, n_pix, d_depths, conf, idx, idx_bytes, depth); \
       ctx->launches++;                                                                                                     \
@@ -635,6 +732,8 @@ int emvs_context_create(int device, emvs_context** out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_merge[b], cudaEventDisableTiming);
   }
   if (const char* env = getenv("EMVS_OVERLAP")) ctx->overlap = atoi(env) != 0;
+  if (const char* env = getenv("EMVS_VOTE_KERNEL")) ctx->vote_tma = strcmp(env, "classic") != 0;
+  if (const char* env = getenv("EMVS_VOTE_CTAS_PER_SM")) ctx->vote_ctas_per_sm = (uint32_t)std::min(8, std::max(1, atoi(env)));
   if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming);
@@ -688,6 +787,7 @@ static void context_release(emvs_context* ctx)
     if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_xy0);
+  cudaFree(ctx->d_work);
   cudaFree(ctx->d_out);
   cudaFree(ctx->d_fc_part);
   cudaFree(ctx->d_partial);
@@ -725,28 +825,6 @@ int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t 
   return EMVS_OK;
 }
 
-static int stage_events(emvs_context* ctx, size_t n_events);
-static int stage_packets(emvs_context* ctx, size_t n_packets_cap, unsigned* par_out);
-
-int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, size_t n_events)
-{
-  REQUIRE(ctx && events && n_events, EMVS_ERR_INVALID, "prefetch_events: NULL argument or empty list");
-  DeviceGuard guard(ctx->device);
-  ctx->prefetch.valid = false;          // an earlier, unconsumed prefetch is dropped: its buffer is free again
-  const int keep = ctx->cur_events;     // stage_events moves cur_events; the current build keeps its own buffer
-  const int rc = stage_events(ctx, n_events);
-  const int buf = ctx->cur_events;
-  ctx->cur_events = keep;
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_events[buf], events, n_events * sizeof(emvs_event), cudaMemcpyHostToDevice, ctx->copy_stream));
-  ctx->prefetch.host = events;
-  ctx->prefetch.n = n_events;
-  ctx->prefetch.buf = buf;
-  ctx->prefetch.valid = true;
-  ctx->prefetch.has_packets = false;
-  return EMVS_OK;
-}
-
 int emvs_selftest_division(emvs_context* ctx, uint64_t n_pairs, uint32_t seed, uint64_t* mismatches)
 {
   REQUIRE(ctx && mismatches, EMVS_ERR_INVALID, "selftest_division: NULL argument");
@@ -762,46 +840,6 @@ int emvs_selftest_division(emvs_context* ctx, uint64_t n_pairs, uint32_t seed, u
   CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   *mismatches = bad;
-  return EMVS_OK;
-}
-
-int emvs_mapper_prefetch_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_stamped_pose* traj,
-                             size_t n_poses, const emvs_pose* T_rv_w)
-{
-  REQUIRE(m && events && traj && T_rv_w, EMVS_ERR_INVALID, "prefetch_dsi: NULL argument");
-  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
-  if (n_events < EMVS_PACKET_SIZE) return EMVS_OK;   // the later evaluateDSI returns false without touching the device
-  emvs_context* ctx = m->ctx;
-  DeviceGuard guard(ctx->device);
-  // the pinned packet buffer of an earlier prefetch may still be in flight
-  if (ctx->prefetched_recorded) CUDA_TRY(cudaEventSynchronize(ctx->ev_prefetched));
-  int rc = emvs_context_prefetch_events(ctx, events, n_events);
-  if (rc) return rc;
-  const size_t max_pk = n_events / EMVS_PACKET_SIZE + 1;
-  if (max_pk > ctx->h_packets_pf_cap) {
-    if (ctx->h_packets_pf) CUDA_TRY(cudaFreeHost(ctx->h_packets_pf));
-    ctx->h_packets_pf = nullptr;
-    ctx->h_packets_pf_cap = 0;
-    CUDA_TRY(cudaHostAlloc((void**)&ctx->h_packets_pf, max_pk * sizeof(emvs_packet), cudaHostAllocDefault));
-    ctx->h_packets_pf_cap = max_pk;
-  }
-  const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
-                                     ctx->h_packets_pf, max_pk);
-  unsigned par = 0;
-  rc = stage_packets(ctx, max_pk, &par);
-  if (rc) return rc;
-  if (n_pk)
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], ctx->h_packets_pf, n_pk * sizeof(emvs_packet), cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
-  CUDA_TRY(cudaEventRecord(ctx->ev_prefetched, ctx->copy_stream));
-  ctx->prefetched_recorded = true;
-  ctx->prefetch.has_packets = true;
-  ctx->prefetch.n_pk = n_pk;
-  ctx->prefetch.par = par;
-  ctx->prefetch.mapper = m;
-  ctx->prefetch.traj = traj;
-  ctx->prefetch.n_poses = n_poses;
-  ctx->prefetch.T_rv_w = *T_rv_w;
   return EMVS_OK;
 }
 
@@ -981,7 +1019,9 @@ int emvs_packetize(const emvs_event* events, size_t n_events, const emvs_stamped
     return EMVS_ERR_TOO_FEW;
   }
   REQUIRE(out || max_packets == 0, EMVS_ERR_INVALID, "packetize: out is NULL");
-  *n_packets = host_packetize(events, n_events, traj, n_poses, *T_rv_w, *cam, virt, z0, out, max_packets);
+  bool truncated = false;
+  *n_packets = host_packetize(times_of(events), n_events, traj, n_poses, *T_rv_w, *cam, virt, z0, out, max_packets, &truncated);
+  REQUIRE(!truncated, EMVS_ERR_INVALID, "packetize: max_packets is too small for this list (n_events / 1024 + 1 always suffices)");
   return EMVS_OK;
 }
 
@@ -994,8 +1034,10 @@ int emvs_packetize_range(const emvs_event* events, size_t n_events, const emvs_s
   REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
   REQUIRE(event_limit <= n_events && *cursor <= n_events, EMVS_ERR_INVALID, "packetize_range: cursor / limit past the list");
   REQUIRE(out || max_packets == 0, EMVS_ERR_INVALID, "packetize_range: out is NULL");
-  *n_packets = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, *cam, virt, z0, cursor, event_limit, out,
-                                    max_packets);
+  bool truncated = false;
+  *n_packets = host_packetize_range(times_of(events), n_events, traj, n_poses, *T_rv_w, *cam, virt, z0, cursor, event_limit, out,
+                                    max_packets, &truncated);
+  REQUIRE(!truncated, EMVS_ERR_INVALID, "packetize_range: max_packets is too small for the events up to event_limit");
   return EMVS_OK;
 }
 
@@ -1416,6 +1458,50 @@ static int check_packets(const emvs_packet* pk, size_t n_packets, size_t n_event
   return EMVS_OK;
 }
 
+// A caller's event list in host memory: the 16-byte dvs_msgs::Event structs (the reference's
+// std::vector<dvs_msgs::Event>), or an emvs_events_soa (separate x / y / t arrays).
+struct HostEvents {
+  const emvs_event* aos = nullptr;
+  const uint16_t* x = nullptr;
+  const uint16_t* y = nullptr;
+  const int64_t* t_ns = nullptr;
+  size_t n = 0;
+  bool soa() const { return aos == nullptr; }
+  const void* key() const { return aos ? (const void*)aos : (const void*)x; }
+  EventTimes times() const
+  {
+    EventTimes t;
+    t.aos = aos;
+    t.t_ns = t_ns;
+    return t;
+  }
+};
+
+static HostEvents host_aos(const emvs_event* ev, size_t n)
+{
+  HostEvents h;
+  h.aos = ev;
+  h.n = n;
+  return h;
+}
+
+// SoA lists are staged as [x: n uint16 | pad to 256 B | y: n uint16]
+static size_t soa_pitch(size_t n) { return (n * sizeof(uint16_t) + 255) & ~(size_t)255; }
+static size_t staging_bytes(const HostEvents& ev) { return ev.soa() ? 2 * soa_pitch(ev.n) : ev.n * sizeof(emvs_event); }
+
+static EventSrc device_src(const emvs_context* ctx, const HostEvents& ev, int buf)
+{
+  EventSrc d;
+  char* base = (char*)ctx->d_events[buf];
+  if (ev.soa()) {
+    d.x = (const uint16_t*)base;
+    d.y = (const uint16_t*)(base + soa_pitch(ev.n));
+  } else {
+    d.aos = (const emvs_event*)base;
+  }
+  return d;
+}
+
 // Host-buffer build.  Staging protocol (one context = one in-order pipeline):
 //   copy_stream:  wait(ev_consumed of the staging buffer's previous build) -> H2D events, packets -> record ev_copied
 //   stream:       wait(ev_copied) -> k_warp_events -> record ev_consumed -> slab loop
@@ -1426,22 +1512,43 @@ static int check_packets(const emvs_packet* pk, size_t n_packets, size_t n_event
 // which is stream-ordered behind the last vote of build N.
 // Picks the staging buffer of the next upload (never the one that holds a pending prefetch), sizes it for the
 // list and orders the copy stream behind the last event stage that read it.  It becomes the current buffer.
-static int stage_events(emvs_context* ctx, size_t n_events)
+static int stage_events(emvs_context* ctx, size_t bytes)
 {
   int u = (int)(ctx->upload_next & 1u);
   if (ctx->prefetch.valid && ctx->prefetch.buf == u) u ^= 1;
   ctx->upload_next = (unsigned)u + 1u;
-  const int rc = grow(&ctx->d_events[u], &ctx->events_cap[u], n_events * sizeof(emvs_event));
+  if (bytes > ctx->events_cap[u] && ctx->consumed_recorded[u]) {
+    // growing frees the old buffer: the event stage that may still be reading it must have finished (cudaFree would
+    // wait for the whole device anyway; this keeps the wait to the one kernel concerned)
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_consumed[u]));
+  }
+  const int rc = grow(&ctx->d_events[u], &ctx->events_cap[u], bytes);
   if (rc) return rc;
   if (ctx->consumed_recorded[u]) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[u], 0));
   ctx->cur_events = u;
   return EMVS_OK;
 }
 
-// A list announced with emvs_context_prefetch_events is already in (or on its way to) a staging buffer.
-static bool take_prefetch(emvs_context* ctx, const emvs_event* events, size_t n_events)
+static bool prefetch_matches(const emvs_context* ctx, const HostEvents& ev)
 {
-  if (!ctx->prefetch.valid || ctx->prefetch.host != events || ctx->prefetch.n != n_events) return false;
+  return ctx->prefetch.valid && ctx->prefetch.host == ev.key() && ctx->prefetch.n == ev.n && ctx->prefetch.soa == ev.soa();
+}
+
+// A pending prefetch is consumed by the NEXT host-buffer build / evaluate call on the context if that call names the
+// same list, and dropped otherwise: a stale announcement can never be matched to some later, unrelated list that
+// happens to live at the same address (its staging buffer is simply reused).
+static void drop_unmatched_prefetch(emvs_context* ctx, const HostEvents& ev)
+{
+  if (ctx->prefetch.valid && !prefetch_matches(ctx, ev)) {
+    ctx->prefetch.valid = false;
+    ctx->prefetch.has_packets = false;
+  }
+}
+
+// A list announced with emvs_context_prefetch_events is already in (or on its way to) a staging buffer.
+static bool take_prefetch(emvs_context* ctx, const HostEvents& ev)
+{
+  if (!prefetch_matches(ctx, ev)) return false;
   ctx->prefetch.valid = false;
   ctx->prefetch.has_packets = false;
   ctx->cur_events = ctx->prefetch.buf;
@@ -1454,6 +1561,8 @@ static int stage_packets(emvs_context* ctx, size_t n_packets_cap, unsigned* par_
 {
   unsigned par = ctx->cur_packets ^ 1u;   // not the one the latest build is voting from
   if (ctx->prefetch.valid && ctx->prefetch.has_packets && ctx->prefetch.par == par) par ^= 1u;
+  if (n_packets_cap * sizeof(emvs_packet) > ctx->packets_cap[par] && ctx->pk_free_recorded[par])
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_pk_free[par]));   // see stage_events
   const int rc = grow(&ctx->d_packets[par], &ctx->packets_cap[par], n_packets_cap * sizeof(emvs_packet));
   if (rc) return rc;
   if (ctx->pk_free_recorded[par]) CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pk_free[par], 0));
@@ -1461,37 +1570,50 @@ static int stage_packets(emvs_context* ctx, size_t n_packets_cap, unsigned* par_
   return EMVS_OK;
 }
 
-static int upload_events(emvs_context* ctx, const emvs_event* events, size_t n_events, size_t lo, size_t hi)
+// enqueue the host -> device copy of events [lo, hi) into the current staging buffer
+static int copy_event_range(emvs_context* ctx, const HostEvents& ev, size_t lo, size_t hi)
 {
-  const int rc = stage_events(ctx, n_events);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events[ctx->cur_events] + lo, events + lo, (hi - lo) * sizeof(emvs_event),
-                           cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (hi <= lo) return EMVS_OK;
+  char* base = (char*)ctx->d_events[ctx->cur_events];
+  if (ev.soa()) {
+    CUDA_TRY(cudaMemcpyAsync(base + lo * 2, ev.x + lo, (hi - lo) * 2, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(base + soa_pitch(ev.n) + lo * 2, ev.y + lo, (hi - lo) * 2, cudaMemcpyHostToDevice, ctx->copy_stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(base + lo * sizeof(emvs_event), ev.aos + lo, (hi - lo) * sizeof(emvs_event), cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+  }
   return EMVS_OK;
 }
 
+static int upload_events(emvs_context* ctx, const HostEvents& ev, size_t lo, size_t hi)
+{
+  const int rc = stage_events(ctx, staging_bytes(ev));
+  if (rc) return rc;
+  return copy_event_range(ctx, ev, lo, hi);
+}
+
 // tail_lo < tail_hi: events [tail_lo, tail_hi) are enqueued for upload right after this build's packets and before
-// its kernels are launched (split upload of emvs_mapper_evaluate_dsi_flags: the copy engine never idles while the
-// host launches the head's kernels).
-static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
-                           size_t n_packets, int flags, bool events_uploaded, size_t tail_lo = 0, size_t tail_hi = 0)
+// its kernels are launched (split upload of evaluate_dsi: the copy engine never idles while the host launches
+// the head's kernels).
+static int build_from_host(emvs_mapper* m, const HostEvents& ev, const emvs_packet* packets, size_t n_packets, int flags,
+                           bool events_uploaded, size_t tail_lo = 0, size_t tail_hi = 0)
 {
   emvs_context* ctx = m->ctx;
   unsigned par = 0;
   {
     // sized for the whole list so that head / tail / whole-list builds alternating over the two buffers never regrow them
-    const int rc = stage_packets(ctx, std::max(n_packets, n_events / EMVS_PACKET_SIZE + 1), &par);
+    const int rc = stage_packets(ctx, std::max(n_packets, ev.n / EMVS_PACKET_SIZE + 1), &par);
     if (rc) return rc;
   }
   ctx->cur_packets = par;
   if (n_packets) {
-    if (!events_uploaded && !take_prefetch(ctx, events, n_events)) {
-      size_t lo = n_events, last = 0;   // only the span of events that packets reference has to travel
+    if (!events_uploaded && !take_prefetch(ctx, ev)) {
+      size_t lo = ev.n, last = 0;   // only the span of events that packets reference has to travel
       for (size_t j = 0; j < n_packets; ++j) {
         lo = std::min<size_t>(lo, packets[j].first_event);
         last = std::max<size_t>(last, packets[j].first_event + EMVS_PACKET_SIZE);
       }
-      const int rc = upload_events(ctx, events, n_events, lo, last);
+      const int rc = upload_events(ctx, ev, lo, last);
       if (rc) return rc;
     }
     CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], packets, n_packets * sizeof(emvs_packet), cudaMemcpyHostToDevice,
@@ -1499,69 +1621,93 @@ static int build_from_host(emvs_mapper* m, const emvs_event* events, size_t n_ev
     CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
   }
-  if (tail_hi > tail_lo)
-    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events[ctx->cur_events] + tail_lo, events + tail_lo, (tail_hi - tail_lo) * sizeof(emvs_event),
-                             cudaMemcpyHostToDevice, ctx->copy_stream));
+  {
+    const int rc = copy_event_range(ctx, ev, tail_lo, tail_hi);
+    if (rc) return rc;
+  }
   ctx->mark_consumed = true;
-  const int rc = build_on_device(m, (const emvs_event*)ctx->d_events[ctx->cur_events], n_events, (const emvs_packet*)ctx->d_packets[par],
-                                 n_packets, flags);
+  const int rc = build_on_device(m, device_src(ctx, ev, ctx->cur_events), ev.n, (const emvs_packet*)ctx->d_packets[par], n_packets,
+                                 flags);
   ctx->mark_consumed = false;
   if (rc) return rc;
   if (n_packets) CUDA_TRY(cudaEventSynchronize(ctx->ev_copied));
   return EMVS_OK;
 }
 
-int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
-                      size_t n_packets, int flags)
+static int ensure_pinned_packets(emvs_packet** p, size_t* cap, size_t need)
 {
-  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
-  REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build: rectification LUT not set (emvs_mapper_set_lut)");
-  REQUIRE(n_packets == 0 || (events && packets), EMVS_ERR_INVALID, "mapper_build: NULL events/packets");
-  int rc = check_packets(packets, n_packets, n_events);
+  if (need <= *cap) return EMVS_OK;
+  if (*p) CUDA_TRY(cudaFreeHost(*p));
+  *p = nullptr;
+  *cap = 0;
+  CUDA_TRY(cudaHostAlloc((void**)p, need * sizeof(emvs_packet), cudaHostAllocDefault));
+  *cap = need;
+  return EMVS_OK;
+}
+
+static int prefetch_events_impl(emvs_context* ctx, const HostEvents& ev)
+{
+  ctx->prefetch.valid = false;          // an earlier, unconsumed prefetch is dropped: its buffer is free again
+  ctx->prefetch.has_packets = false;
+  const int keep = ctx->cur_events;     // stage_events moves cur_events; the current build keeps its own buffer
+  int rc = stage_events(ctx, staging_bytes(ev));
+  const int buf = ctx->cur_events;
+  if (!rc) rc = copy_event_range(ctx, ev, 0, ev.n);
+  ctx->cur_events = keep;
   if (rc) return rc;
-  DeviceGuard guard(m->ctx->device);
-  return build_from_host(m, events, n_events, packets, n_packets, flags, false);
+  ctx->prefetch.host = ev.key();
+  ctx->prefetch.soa = ev.soa();
+  ctx->prefetch.n = ev.n;
+  ctx->prefetch.buf = buf;
+  ctx->prefetch.valid = true;
+  ctx->prefetch.generation = ++ctx->prefetch_generation;
+  return EMVS_OK;
 }
 
-int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_events, const void* d_packets,
-                             size_t n_packets, int flags)
+static int prefetch_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_stamped_pose* traj, size_t n_poses,
+                             const emvs_pose* T_rv_w)
 {
-  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
-  REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build_device: rectification LUT not set (emvs_mapper_set_lut)");
-  REQUIRE(n_packets == 0 || (d_events && d_packets), EMVS_ERR_INVALID, "mapper_build_device: NULL events/packets");
-  DeviceGuard guard(m->ctx->device);
-  return build_on_device(m, (const emvs_event*)d_events, n_events, (const emvs_packet*)d_packets, n_packets, flags);
-}
-
-int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
-                             const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w)
-{
-  return emvs_mapper_evaluate_dsi_flags(m, events, n_events, traj, n_poses, T_rv_w, EMVS_BUILD_RESET);
-}
-
-int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, size_t n_events,
-                                   const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w, int flags)
-{
-  REQUIRE(m && events && traj && T_rv_w, EMVS_ERR_INVALID, "evaluate_dsi: NULL argument");
-  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
-  if (n_events < EMVS_PACKET_SIZE) {
-    set_error("Number of events (%zu) < packet size (%d)", n_events, EMVS_PACKET_SIZE);
-    return EMVS_ERR_TOO_FEW;
-  }
   emvs_context* ctx = m->ctx;
-  DeviceGuard guard(ctx->device);
+  // the pinned packet buffer of an earlier prefetch may still be in flight
+  if (ctx->prefetched_recorded) CUDA_TRY(cudaEventSynchronize(ctx->ev_prefetched));
+  int rc = prefetch_events_impl(ctx, ev);
+  if (rc) return rc;
+  const size_t max_pk = ev.n / EMVS_PACKET_SIZE + 1;
+  rc = ensure_pinned_packets(&ctx->h_packets_pf, &ctx->h_packets_pf_cap, max_pk);
+  if (rc) return rc;
+  const size_t n_pk = host_packetize(ev.times(), ev.n, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], ctx->h_packets_pf,
+                                     max_pk);
+  unsigned par = 0;
+  rc = stage_packets(ctx, max_pk, &par);
+  if (rc) return rc;
+  if (n_pk)
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_packets[par], ctx->h_packets_pf, n_pk * sizeof(emvs_packet), cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+  CUDA_TRY(cudaEventRecord(ctx->ev_prefetched, ctx->copy_stream));
+  ctx->prefetched_recorded = true;
+  ctx->prefetch.has_packets = true;
+  ctx->prefetch.n_pk = n_pk;
+  ctx->prefetch.par = par;
+  ctx->prefetch.mapper = m;
+  ctx->prefetch.traj = traj;
+  ctx->prefetch.n_poses = n_poses;
+  ctx->prefetch.T_rv_w = *T_rv_w;
+  return EMVS_OK;
+}
+
+// Whole evaluateDSI for an event list in host memory (AoS or SoA).
+static int evaluate_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_stamped_pose* traj, size_t n_poses,
+                             const emvs_pose* T_rv_w, int flags)
+{
+  emvs_context* ctx = m->ctx;
+  const size_t n_events = ev.n;
   const size_t max_pk = n_events / EMVS_PACKET_SIZE + 1;
-  if (max_pk > ctx->h_packets_cap) {
-    if (ctx->h_packets) CUDA_TRY(cudaFreeHost(ctx->h_packets));
-    ctx->h_packets = nullptr;
-    ctx->h_packets_cap = 0;
-    CUDA_TRY(cudaHostAlloc((void**)&ctx->h_packets, max_pk * sizeof(emvs_packet), cudaHostAllocDefault));
-    ctx->h_packets_cap = max_pk;
-  }
-  REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi: rectification LUT not set (emvs_mapper_set_lut)");
-  if (ctx->prefetch.valid && ctx->prefetch.has_packets && ctx->prefetch.host == events && ctx->prefetch.n == n_events &&
-      ctx->prefetch.mapper == m && ctx->prefetch.traj == traj && ctx->prefetch.n_poses == n_poses &&
-      std::memcmp(&ctx->prefetch.T_rv_w, T_rv_w, sizeof(emvs_pose)) == 0) {
+  int rc = ensure_pinned_packets(&ctx->h_packets, &ctx->h_packets_cap, max_pk);
+  if (rc) return rc;
+  drop_unmatched_prefetch(ctx, ev);
+  const EventTimes times = ev.times();
+  if (prefetch_matches(ctx, ev) && ctx->prefetch.has_packets && ctx->prefetch.mapper == m && ctx->prefetch.traj == traj &&
+      ctx->prefetch.n_poses == n_poses && std::memcmp(&ctx->prefetch.T_rv_w, T_rv_w, sizeof(emvs_pose)) == 0) {
     // emvs_mapper_prefetch_dsi ran for exactly this call: events and packets are in HBM (or landing), only the
     // kernels are left
     ctx->prefetch.valid = false;
@@ -1570,19 +1716,18 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
     ctx->cur_packets = ctx->prefetch.par;
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetched, 0));
     ctx->mark_consumed = true;
-    const int rc = build_on_device(m, (const emvs_event*)ctx->d_events[ctx->cur_events], n_events,
-                                   (const emvs_packet*)ctx->d_packets[ctx->cur_packets], ctx->prefetch.n_pk, flags);
+    rc = build_on_device(m, device_src(ctx, ev, ctx->cur_events), n_events, (const emvs_packet*)ctx->d_packets[ctx->cur_packets],
+                         ctx->prefetch.n_pk, flags);
     ctx->mark_consumed = false;
     if (rc) return rc;
-    CUDA_TRY(cudaEventSynchronize(ctx->ev_prefetched));   // the caller may reuse `events` on return
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_prefetched));   // the caller may reuse its list on return
     return EMVS_OK;
   }
-  if (take_prefetch(ctx, events, n_events)) {
+  if (take_prefetch(ctx, ev)) {
     // the list was announced earlier (emvs_context_prefetch_events): nothing to upload, the packet stage is all
     // that stands between the call and the first vote
-    const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
-                                       ctx->h_packets, max_pk);
-    const int rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, flags, true);
+    const size_t n_pk = host_packetize(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], ctx->h_packets, max_pk);
+    rc = build_from_host(m, ev, ctx->h_packets, n_pk, flags, true);
     if (rc) return rc;
     if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return EMVS_OK;
@@ -1601,45 +1746,193 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
     else if (q == cudaErrorNotReady) (void)cudaGetLastError();   // "busy" is an answer, not an error: do not leave it behind
     else CUDA_TRY(q);
   }
-  int rc;
   if (n_head >= EMVS_PACKET_SIZE) {
-    rc = upload_events(ctx, events, n_events, 0, n_head);
+    rc = upload_events(ctx, ev, 0, n_head);
     if (rc) return rc;
     size_t cur = 0;
-    const size_t n_pk_head = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
-                                                  &cur, n_head, ctx->h_packets, max_pk);
+    const size_t n_pk_head = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
+                                                  n_head, ctx->h_packets, max_pk);
     if (n_pk_head) {
-      rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk_head, flags, true, n_head, n_events);
+      rc = build_from_host(m, ev, ctx->h_packets, n_pk_head, flags, true, n_head, n_events);
       if (rc) return rc;
-      const size_t n_pk_tail = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
-                                                    &cur, n_events, ctx->h_packets + n_pk_head, max_pk - n_pk_head);
+      const size_t n_pk_tail = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
+                                                    n_events, ctx->h_packets + n_pk_head, max_pk - n_pk_head);
       if (n_pk_tail) {
-        rc = build_from_host(m, events, n_events, ctx->h_packets + n_pk_head, n_pk_tail, flags | EMVS_BUILD_ACCUMULATE, true);
+        rc = build_from_host(m, ev, ctx->h_packets + n_pk_head, n_pk_tail, flags | EMVS_BUILD_ACCUMULATE, true);
         if (rc) return rc;
       } else {
-        CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse `events` on return
+        CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse its list on return
       }
       return EMVS_OK;
     }
     // no packet in the head (every pose lookup missed): upload the rest and build in one piece
-    CUDA_TRY(cudaMemcpyAsync((emvs_event*)ctx->d_events[ctx->cur_events] + n_head, events + n_head, (n_events - n_head) * sizeof(emvs_event),
-                             cudaMemcpyHostToDevice, ctx->copy_stream));
-    const size_t n_pk = host_packetize_range(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
-                                             n_events, ctx->h_packets, max_pk);
-    rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, flags, true);
+    rc = copy_event_range(ctx, ev, n_head, n_events);
+    if (rc) return rc;
+    const size_t n_pk = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur, n_events,
+                                             ctx->h_packets, max_pk);
+    rc = build_from_host(m, ev, ctx->h_packets, n_pk, flags, true);
     if (rc) return rc;
     if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return EMVS_OK;
   }
   // start the event upload first: the host packet stage (one pose + one 3x3 inverse per 1024
   // events) then runs while the copy engine is busy
-  rc = upload_events(ctx, events, n_events, 0, n_events);
+  rc = upload_events(ctx, ev, 0, n_events);
   if (rc) return rc;
-  const size_t n_pk = host_packetize(events, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0],
-                                     ctx->h_packets, max_pk);
-  rc = build_from_host(m, events, n_events, ctx->h_packets, n_pk, flags, true);
+  const size_t n_pk = host_packetize(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], ctx->h_packets, max_pk);
+  rc = build_from_host(m, ev, ctx->h_packets, n_pk, flags, true);
   if (rc) return rc;
   if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // nothing waited for the event upload
+  return EMVS_OK;
+}
+
+static int check_soa(const emvs_events_soa* ev, const char* who)
+{
+  if (!ev || !ev->x || !ev->y || !ev->t_ns) {
+    set_error("%s: NULL event arrays", who);
+    return EMVS_ERR_INVALID;
+  }
+  return EMVS_OK;
+}
+
+static HostEvents host_soa(const emvs_events_soa* ev)
+{
+  HostEvents h;
+  h.x = ev->x;
+  h.y = ev->y;
+  h.t_ns = ev->t_ns;
+  h.n = ev->n;
+  return h;
+}
+
+int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, size_t n_events)
+{
+  REQUIRE(ctx && events && n_events, EMVS_ERR_INVALID, "prefetch_events: NULL argument or empty list");
+  DeviceGuard guard(ctx->device);
+  return prefetch_events_impl(ctx, host_aos(events, n_events));
+}
+
+int emvs_context_prefetch_pending(emvs_context* ctx, uint64_t* generation)
+{
+  REQUIRE(ctx && generation, EMVS_ERR_INVALID, "prefetch_pending: NULL argument");
+  *generation = ctx->prefetch.valid ? ctx->prefetch.generation : 0;
+  return EMVS_OK;
+}
+
+int emvs_context_prefetch_cancel(emvs_context* ctx)
+{
+  REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(ctx->device);
+  if (ctx->prefetch.valid) {
+    // the copies may still be reading the caller's arrays: after this call they are the caller's again
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->prefetch.valid = false;
+    ctx->prefetch.has_packets = false;
+  }
+  return EMVS_OK;
+}
+
+int emvs_mapper_prefetch_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_stamped_pose* traj,
+                             size_t n_poses, const emvs_pose* T_rv_w)
+{
+  REQUIRE(m && events && traj && T_rv_w, EMVS_ERR_INVALID, "prefetch_dsi: NULL argument");
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  if (n_events < EMVS_PACKET_SIZE) return EMVS_OK;   // the later evaluateDSI returns false without touching the device
+  DeviceGuard guard(m->ctx->device);
+  return prefetch_dsi_impl(m, host_aos(events, n_events), traj, n_poses, T_rv_w);
+}
+
+int emvs_mapper_prefetch_dsi_soa(emvs_mapper* m, const emvs_events_soa* events, const emvs_stamped_pose* traj, size_t n_poses,
+                                 const emvs_pose* T_rv_w)
+{
+  REQUIRE(m && traj && T_rv_w, EMVS_ERR_INVALID, "prefetch_dsi_soa: NULL argument");
+  int rc = check_soa(events, "prefetch_dsi_soa");
+  if (rc) return rc;
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  if (events->n < EMVS_PACKET_SIZE) return EMVS_OK;
+  DeviceGuard guard(m->ctx->device);
+  return prefetch_dsi_impl(m, host_soa(events), traj, n_poses, T_rv_w);
+}
+
+int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events, const emvs_packet* packets,
+                      size_t n_packets, int flags)
+{
+  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
+  REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE(n_packets == 0 || (events && packets), EMVS_ERR_INVALID, "mapper_build: NULL events/packets");
+  int rc = check_packets(packets, n_packets, n_events);
+  if (rc) return rc;
+  DeviceGuard guard(m->ctx->device);
+  const HostEvents ev = host_aos(events, n_events);
+  drop_unmatched_prefetch(m->ctx, ev);
+  return build_from_host(m, ev, packets, n_packets, flags, false);
+}
+
+int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_events, const void* d_packets,
+                             size_t n_packets, int flags)
+{
+  REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
+  REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build_device: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE(n_packets == 0 || (d_events && d_packets), EMVS_ERR_INVALID, "mapper_build_device: NULL events/packets");
+  DeviceGuard guard(m->ctx->device);
+  EventSrc src;
+  src.aos = (const emvs_event*)d_events;
+  return build_on_device(m, src, n_events, (const emvs_packet*)d_packets, n_packets, flags);
+}
+
+int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                             const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w)
+{
+  return emvs_mapper_evaluate_dsi_flags(m, events, n_events, traj, n_poses, T_rv_w, EMVS_BUILD_RESET);
+}
+
+int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, size_t n_events,
+                                   const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w, int flags)
+{
+  REQUIRE(m && events && traj && T_rv_w, EMVS_ERR_INVALID, "evaluate_dsi: NULL argument");
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  if (n_events < EMVS_PACKET_SIZE) {
+    set_error("Number of events (%zu) < packet size (%d)", n_events, EMVS_PACKET_SIZE);
+    return EMVS_ERR_TOO_FEW;
+  }
+  REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi: rectification LUT not set (emvs_mapper_set_lut)");
+  DeviceGuard guard(m->ctx->device);
+  return evaluate_dsi_impl(m, host_aos(events, n_events), traj, n_poses, T_rv_w, flags);
+}
+
+int emvs_mapper_evaluate_dsi_soa(emvs_mapper* m, const emvs_events_soa* events, const emvs_stamped_pose* traj, size_t n_poses,
+                                 const emvs_pose* T_rv_w, int flags)
+{
+  REQUIRE(m && traj && T_rv_w, EMVS_ERR_INVALID, "evaluate_dsi_soa: NULL argument");
+  int rc = check_soa(events, "evaluate_dsi_soa");
+  if (rc) return rc;
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  if (events->n < EMVS_PACKET_SIZE) {
+    set_error("Number of events (%zu) < packet size (%d)", events->n, EMVS_PACKET_SIZE);
+    return EMVS_ERR_TOO_FEW;
+  }
+  REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi_soa: rectification LUT not set (emvs_mapper_set_lut)");
+  DeviceGuard guard(m->ctx->device);
+  return evaluate_dsi_impl(m, host_soa(events), traj, n_poses, T_rv_w, flags);
+}
+
+int emvs_packetize_soa(const emvs_events_soa* events, const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w,
+                       const emvs_camera* cam, const float virt[4], float z0, emvs_packet* out, size_t max_packets,
+                       size_t* n_packets)
+{
+  REQUIRE(traj && T_rv_w && cam && virt && n_packets, EMVS_ERR_INVALID, "packetize_soa: NULL argument");
+  int rc = check_soa(events, "packetize_soa");
+  if (rc) return rc;
+  REQUIRE(n_poses >= 2, EMVS_ERR_INVALID, "At least two poses need to be provided");
+  *n_packets = 0;
+  if (events->n < EMVS_PACKET_SIZE) {
+    set_error("Number of events (%zu) < packet size (%d)", events->n, EMVS_PACKET_SIZE);
+    return EMVS_ERR_TOO_FEW;
+  }
+  REQUIRE(out || max_packets == 0, EMVS_ERR_INVALID, "packetize_soa: out is NULL");
+  bool truncated = false;
+  *n_packets = host_packetize(host_soa(events).times(), events->n, traj, n_poses, *T_rv_w, *cam, virt, z0, out, max_packets, &truncated);
+  REQUIRE(!truncated, EMVS_ERR_INVALID, "packetize_soa: max_packets is too small for this list (n_events / 1024 + 1 always suffices)");
   return EMVS_OK;
 }
 

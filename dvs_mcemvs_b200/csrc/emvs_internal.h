@@ -20,12 +20,32 @@ void host_pose_compose(const emvs_pose& a, const emvs_pose& b, emvs_pose* out);
 void host_pose_inverse(const emvs_pose& a, emvs_pose* out);
 int host_rectify_lut(int model, const double K[9], const double* D, int n_d, const double R[9], const double P[12],
                      uint32_t W, uint32_t H, float* out);
-size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+// Where the packet stage reads an event's timestamp (the only event field the host touches): the 16-byte
+// dvs_msgs::Event structs, or the int64 nanosecond array of an emvs_events_soa.
+struct EventTimes {
+  const emvs_event* aos = nullptr;
+  const int64_t* t_ns = nullptr;
+  void at(size_t i, uint32_t* sec, uint32_t* nsec) const
+  {
+    if (aos) {
+      *sec = aos[i].sec;
+      *nsec = aos[i].nsec;
+    } else {
+      const int64_t t = t_ns[i];
+      *sec = (uint32_t)(t / 1000000000ll);
+      *nsec = (uint32_t)(t % 1000000000ll);
+    }
+  }
+};
+inline EventTimes times_of(const emvs_event* ev) { EventTimes t; t.aos = ev; return t; }
+// *truncated (may be NULL) is set when the loop stopped because `max_out` packets were written while more would fit.
+size_t host_packetize(const EventTimes& ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
                       const emvs_pose& T_rv_w, const emvs_camera& cam, const float virt[4], float z0,
-                      emvs_packet* out, size_t max_out);
-size_t host_packetize_range(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+                      emvs_packet* out, size_t max_out, bool* truncated = nullptr);
+size_t host_packetize_range(const EventTimes& ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
                             const emvs_pose& T_rv_w, const emvs_camera& cam, const float virt[4], float z0,
-                            size_t* cur_inout, size_t event_limit, emvs_packet* out, size_t max_out);
+                            size_t* cur_inout, size_t event_limit, emvs_packet* out, size_t max_out,
+                            bool* truncated = nullptr);
 
 // nccl_dl.cpp — NCCL resolved at run time so the library loads (and every single-GPU entry
 // point works) on machines without NCCL, and shares torch's NCCL when loaded from Python.

@@ -314,12 +314,12 @@ int host_rectify_lut(int model, const double K[9], const double* D, int n_d, con
   return 0;
 }
 
-size_t host_packetize(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+size_t host_packetize(const EventTimes& ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
                       const emvs_pose& T_rv_w_pod, const emvs_camera& cam, const float virt[4], float z0,
-                      emvs_packet* out, size_t max_out)
+                      emvs_packet* out, size_t max_out, bool* truncated)
 {
   size_t cur = 0;
-  return host_packetize_range(ev, n_ev, traj, n_poses, T_rv_w_pod, cam, virt, z0, &cur, n_ev, out, max_out);
+  return host_packetize_range(ev, n_ev, traj, n_poses, T_rv_w_pod, cam, virt, z0, &cur, n_ev, out, max_out, truncated);
 }
 
 namespace {
@@ -331,12 +331,13 @@ struct PacketStage {   // per-call constants of the packet loop
 };
 
 // One iteration of mapper_emvs_stereo.cpp:91-120 for the packet that starts at event `cur`: false on a pose miss.
-inline bool make_packet(const PacketStage& S, const emvs_event* ev, size_t cur, const emvs_stamped_pose* traj, size_t n_poses,
+inline bool make_packet(const PacketStage& S, const EventTimes& ev, size_t cur, const emvs_stamped_pose* traj, size_t n_poses,
                         emvs_packet* pk)
 {
-  const emvs_event& mid = ev[cur + EMVS_PACKET_SIZE / 2];
+  uint32_t mid_sec, mid_nsec;
+  ev.at(cur + EMVS_PACKET_SIZE / 2, &mid_sec, &mid_nsec);
   SE3 T_w_ev;
-  if (!interpolate(traj, n_poses, mid.sec, mid.nsec, &T_w_ev)) return false;
+  if (!interpolate(traj, n_poses, mid_sec, mid_nsec, &T_w_ev)) return false;
   const SE3 T_ev_rv = (S.T_rv_w * T_w_ev).inverse();
   double Rd[3][3];
   T_ev_rv.q.to_matrix(Rd);
@@ -381,9 +382,9 @@ unsigned packet_threads()
 // longest all-successful prefix is kept — exactly what the sequential loop would have produced; at the first miss
 // the loop continues sequentially from there.  (One pose interpolation + two 3x3 inverses per packet: 1.4 ms per
 // 5 M events on one core, which is what a prefetched or device-resident caller waits for.)
-size_t host_packetize_range(const emvs_event* ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
+size_t host_packetize_range(const EventTimes& ev, size_t n_ev, const emvs_stamped_pose* traj, size_t n_poses,
                             const emvs_pose& T_rv_w_pod, const emvs_camera& cam, const float virt[4], float z0,
-                            size_t* cur_inout, size_t event_limit, emvs_packet* out, size_t max_out)
+                            size_t* cur_inout, size_t event_limit, emvs_packet* out, size_t max_out, bool* truncated)
 {
   PacketStage S;
   S.K = pinhole_K(cam.fx, cam.fy, cam.cx, cam.cy);
@@ -408,24 +409,43 @@ size_t host_packetize_range(const emvs_event* ev, size_t n_ev, const emvs_stampe
       size_t n_fit = (last - cur) / EMVS_PACKET_SIZE;
       n_fit = std::min(n_fit, max_out - produced);
       if (n_fit >= kMinBatch) {
-        std::vector<size_t> first_miss(T, n_fit);
+        // This code is reached from extern "C" entry points that never throw: a failed allocation or thread start
+        // (std::bad_alloc, std::system_error at the thread limit) must not cross the C ABI.  Workers that did start
+        // are always joined; whatever could not be started is simply not done speculatively — the sequential loop
+        // below recomputes it, so the result is the same.
+        constexpr unsigned kMaxT = 64;
+        const unsigned Tn = std::min(T, kMaxT);
+        size_t first_miss[kMaxT];
+        for (unsigned w = 0; w < Tn; ++w) first_miss[w] = n_fit * w / Tn;   // "nothing done" until the worker reports
         auto work = [&](unsigned w) {
-          const size_t lo = n_fit * w / T, hi = n_fit * (w + 1) / T;
-          for (size_t j = lo; j < hi; ++j)
-            if (!make_packet(S, ev, cur + j * EMVS_PACKET_SIZE, traj, n_poses, out + produced + j)) {
-              first_miss[w] = j;
-              break;   // everything after the first miss is recomputed sequentially
-            }
+          const size_t lo = n_fit * w / Tn, hi = n_fit * (w + 1) / Tn;
+          size_t j = lo;
+          for (; j < hi; ++j)
+            if (!make_packet(S, ev, cur + j * EMVS_PACKET_SIZE, traj, n_poses, out + produced + j)) break;
+          first_miss[w] = j;   // == hi when every packet of the range succeeded
         };
-        std::vector<std::thread> pool;
-        pool.reserve(T - 1);
-        for (unsigned w = 1; w < T; ++w) pool.emplace_back(work, w);
+        std::thread pool[kMaxT];
+        unsigned started = 1;   // worker 0 is this thread
+        try {
+          for (unsigned w = 1; w < Tn; ++w) {
+            pool[w] = std::thread(work, w);
+            started = w + 1;
+          }
+        } catch (...) {
+          // fewer workers than planned: the ranges of the missing ones keep first_miss == their lower bound
+        }
         work(0);
-        for (std::thread& t : pool) t.join();
-        const size_t prefix = *std::min_element(first_miss.begin(), first_miss.end());
+        for (unsigned w = 1; w < started; ++w) pool[w].join();
+        // longest all-successful prefix: ranges are contiguous, a range counts fully only if it reached its end
+        size_t prefix = 0;
+        for (unsigned w = 0; w < Tn; ++w) {
+          const size_t hi = n_fit * (w + 1) / Tn;
+          prefix = first_miss[w];
+          if (first_miss[w] < hi) break;
+        }
         produced += prefix;
         cur += prefix * EMVS_PACKET_SIZE;
-        streak = 0;       // either nothing fits any more, or the packet at `cur` missed: go on one by one
+        streak = 0;       // either nothing fits any more, or the packet at `cur` missed / was not computed: go on one by one
         continue;
       }
     }
@@ -439,6 +459,7 @@ size_t host_packetize_range(const emvs_event* ev, size_t n_ev, const emvs_stampe
     }
   }
   *cur_inout = cur;
+  if (truncated) *truncated = produced == max_out && fits(cur);
   return produced;
 }
 

@@ -32,6 +32,15 @@ class Grid3D {
   Grid3D& operator=(const Grid3D& o)
   {
     if (this == &o) return *this;
+    if (g_ && !owned_) {
+      // a mapper-attached dsi_ (MapperEMVS::dsi_): the reference's `mapper.dsi_ = other` overwrites the member the
+      // mapper keeps voting into, so copy INTO the attached volume instead of detaching from it
+      if (!o.g_ || o.size_[0] != size_[0] || o.size_[1] != size_[1] || o.size_[2] != size_[2])
+        throw std::runtime_error("Grid3D: assignment to a mapper's dsi_ needs a grid of the same dimensions");
+      emvs_host::check(emvs_grid_copy(g_, o.g_), "Grid3D copy");
+      mirror_.clear();
+      return *this;
+    }
     deallocate();
     if (o.g_) {
       allocate(o.size_[0], o.size_[1], o.size_[2]);

@@ -194,7 +194,23 @@ class MapperEMVS {
     return true;
   }
 
-  // Streaming callers (main.cpp's full_seq loop): announce the arguments of a LATER evaluateDSI call on this mapper.
+  // Structure-of-arrays event list (x, y, t stored separately, e.g. read from a DSEC / TUM-VIE HDF5 file): same DSI,
+  // a quarter of the PCIe traffic.  No counterpart in the reference, whose only event container is the
+  // std::vector<dvs_msgs::Event> above.
+  bool evaluateDSI(const emvs_events_soa& events, const TrajectoryType& trajectory, const geometry_utils::Transformation& T_rv_w)
+  {
+    dsi_.touch();
+    const int rc = emvs_mapper_evaluate_dsi_soa(m_, &events, trajectory.pods().data(), trajectory.pods().size(), &T_rv_w.pod(),
+                                                EMVS_BUILD_RESET);
+    if (rc == EMVS_ERR_TOO_FEW) {
+      std::cerr << "Number of events ( " << events.n << ") < packet size (" << EMVS_PACKET_SIZE << ")" << std::endl;
+      return false;
+    }
+    emvs_host::check(rc, "evaluateDSI");
+    return true;
+  }
+
+  // Streaming callers (main.cpp's full_seq loop): announce the arguments of the NEXT evaluateDSI call on this mapper.
   // The event upload starts and the host packet stage runs now, under whatever the device is computing; the later
   // evaluateDSI with the same arguments only launches kernels.  `events` and `trajectory` must stay unchanged until then.
   // (No counterpart in the reference: it is what hides PCIe behind the previous window's votes.)

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define EMVS_ABI_VERSION 1
+#define EMVS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define EMVS_API __attribute__((visibility("default")))
@@ -68,6 +68,17 @@ typedef struct emvs_event {
   uint8_t polarity;
   uint8_t pad_[3];
 } emvs_event;
+
+/* Structure-of-arrays event list, as the HDF5 event files of DSEC / TUM-VIE store them (events/x, events/y, events/t)
+ * and as a caller can cheaply keep them: only x and y travel to the device (4 bytes per event instead of the 16-byte
+ * dvs_msgs::Event), the timestamps stay on the host, where the packet stage reads ONE of them per 1024 events
+ * (MAP:91).  t_ns = ros::Time::toNSec() of the event, non-decreasing like the reference's sorted event vector. */
+typedef struct emvs_events_soa {
+  const uint16_t* x;
+  const uint16_t* y;
+  const int64_t* t_ns;
+  size_t n;
+} emvs_events_soa;
 
 /* kindr::minimal::QuatTransformation: unit quaternion (w,x,y,z) + position, double. */
 typedef struct emvs_pose {
@@ -159,12 +170,20 @@ EMVS_API int emvs_context_set_slab(emvs_context* ctx, uint32_t planes_per_slab);
  * shorter than `min_events` are built in one piece; percent = 0 disables.  Defaults: 25 %, 2^20 events
  * ($EMVS_UPLOAD_SPLIT overrides the percentage at context creation). */
 EMVS_API int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t min_events);
-/* Streaming callers (consecutive windows, main.cpp:177-431 full_seq loop): announce the event list of a LATER
- * emvs_mapper_evaluate_dsi / emvs_mapper_build call.  Its host->device copy starts now, on the copy stream, under
- * whatever the context is computing; the later call recognises the list by (pointer, n_events) and skips its own
- * upload.  Returns immediately.  The list must stay valid and unchanged until that call has returned; one
- * prefetch can be pending per context (a new one replaces it); other lists may be built in between. */
+/* Streaming callers (consecutive windows, main.cpp:177-431 full_seq loop): announce the event list of the NEXT
+ * emvs_mapper_evaluate_dsi / emvs_mapper_build call on this context.  Its host->device copy starts now, on the copy
+ * stream, under whatever the context is computing; that next call recognises the list by (pointer, n_events) and
+ * skips its own upload.  Returns immediately.  Lifetime rule: the list must stay valid and unchanged until the
+ * consuming call has returned or the prefetch has been cancelled.  One prefetch can be pending per context (a new
+ * one replaces it); the next host-buffer evaluate / build call either consumes it (same list) or DROPS it (any
+ * other list), so an announcement never outlives that call and can never be matched to an unrelated later list
+ * that happens to be allocated at the same address.  (Builds from device-resident inputs leave it pending.) */
 EMVS_API int emvs_context_prefetch_events(emvs_context* ctx, const emvs_event* events, size_t n_events);
+/* Generation number of the pending prefetch (every prefetch call gets a new one), 0 when none is pending — lets a
+ * caller assert that the announcement it made is the one about to be consumed. */
+EMVS_API int emvs_context_prefetch_pending(emvs_context* ctx, uint64_t* generation);
+/* Withdraws the pending prefetch, if any: waits for its copies, after which the caller owns its arrays again. */
+EMVS_API int emvs_context_prefetch_cancel(emvs_context* ctx);
 /* Device self-test of the vote kernel's shared-divisor division (a prepared reciprocal per (plane, packet) and three
  * FFMAs per numerator instead of a full IEEE division): runs about n_pairs pseudo-random and adversarial operand
  * pairs inside the prepared range through both and returns how many quotients differ in any bit from __fdiv_rn. */
@@ -176,6 +195,8 @@ EMVS_API int emvs_selftest_division(emvs_context* ctx, uint64_t n_pairs, uint32_
  * (or to the ordinary path).  `events` and `traj` must stay valid and unchanged until that call has returned. */
 EMVS_API int emvs_mapper_prefetch_dsi(emvs_mapper* m, const emvs_event* events, size_t n_events,
                              const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w);
+EMVS_API int emvs_mapper_prefetch_dsi_soa(emvs_mapper* m, const emvs_events_soa* events, const emvs_stamped_pose* traj,
+                                 size_t n_poses, const emvs_pose* T_rv_w);
 /* Number of kernels this library launched on the context so far (bench `gpu_launches`). */
 EMVS_API int emvs_context_launch_count(emvs_context* ctx, uint64_t* out);
 /* Per-launch device timing of the vote kernel (the dominant kernel; bench.py's roofline):
@@ -221,11 +242,16 @@ EMVS_API int emvs_pose_inverse(const emvs_pose* a, emvs_pose* out);
 /* Packet stage of evaluateDSI (MAP:86-126): groups events in packets of 1024, one pose per
  * packet at the timestamp of its middle event, skipping one event on a pose miss.  Writes up
  * to max_packets packets and the number produced to *n_packets.  Returns EMVS_ERR_TOO_FEW when
- * n_events < 1024. */
+ * n_events < 1024, and EMVS_ERR_INVALID (with the packets written so far still valid) when max_packets is too
+ * small for the list — n_events / 1024 + 1 always suffices. */
 EMVS_API int emvs_packetize(const emvs_event* events, size_t n_events,
                    const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w,
                    const emvs_camera* cam, const float virt[4], float z0,
                    emvs_packet* out, size_t max_packets, size_t* n_packets);
+/* The same packet stage for a structure-of-arrays list (timestamps from events->t_ns). */
+EMVS_API int emvs_packetize_soa(const emvs_events_soa* events, const emvs_stamped_pose* traj, size_t n_poses,
+                       const emvs_pose* T_rv_w, const emvs_camera* cam, const float virt[4], float z0,
+                       emvs_packet* out, size_t max_packets, size_t* n_packets);
 /* Resumable form for streaming callers: continues the same packet loop from event index *cursor and stops before
  * the first packet that would reach past `event_limit` (events [0, event_limit) are known so far; the full list
  * has n_events).  *cursor is advanced; successive calls with growing limits produce exactly the packets of one
@@ -317,6 +343,10 @@ EMVS_API int emvs_mapper_evaluate_dsi(emvs_mapper* m, const emvs_event* events, 
 /* emvs_mapper_evaluate_dsi with build flags (EMVS_BUILD_ALLREDUCE / EMVS_BUILD_PEER_REDUCE for a rank's shard). */
 EMVS_API int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, size_t n_events,
                                    const emvs_stamped_pose* traj, size_t n_poses, const emvs_pose* T_rv_w, int flags);
+/* MapperEMVS::evaluateDSI (MAP:67-148) for a structure-of-arrays event list: same packets, same votes, same DSI as the
+ * dvs_msgs::Event form with equal x, y and timestamps; a quarter of the PCIe traffic.  flags as above. */
+EMVS_API int emvs_mapper_evaluate_dsi_soa(emvs_mapper* m, const emvs_events_soa* events, const emvs_stamped_pose* traj,
+                                 size_t n_poses, const emvs_pose* T_rv_w, int flags);
 /* Build-defined integer observable: accepted (event, plane k) votes of the last
  * build(s) since the last RESET, one uint64 per plane. */
 EMVS_API int emvs_mapper_counts(const emvs_mapper* m, uint64_t* per_plane /* dimZ */);

@@ -52,6 +52,12 @@ def test_packetize_range_any_limits(O, n, t_lo, span, n_ctrl, cuts, seed, max_pa
     # a bounded output buffer returns the first max_packets packets of the same sequence
     out = np.zeros(max(max_packets, 1), capi.PACKET_DTYPE)
     k = C.c_size_t(0)
-    capi.check(lib.emvs_packetize(capi.ptr(ev), n, capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam), capi.ptr(K), 1.0,
-                                  capi.ptr(out), max_packets, C.byref(k)))
+    rc = lib.emvs_packetize(capi.ptr(ev), n, capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam), capi.ptr(K), 1.0,
+                            capi.ptr(out), max_packets, C.byref(k))
     assert k.value == min(max_packets, len(want)) and out[:k.value].tobytes() == want[:k.value].tobytes()
+    # ... and says so: a list that did not fit is an error (never a silently shortened packet list); when the buffer
+    # was big enough for every packet AND for noticing that nothing is left, the call succeeds
+    if max_packets < len(want):
+        assert rc == capi.EMVS_ERR_INVALID and b"max_packets" in lib.emvs_last_error()
+    elif max_packets > len(want):
+        assert rc == capi.EMVS_OK

@@ -27,7 +27,7 @@ def test_header_symbols_exported():
 def test_python_binding_covers_header():
     assert sorted(capi._PROTOTYPES) == _declared()
     lib = capi.load()
-    assert lib.emvs_abi_version() == 1
+    assert lib.emvs_abi_version() == 2
 
 
 def test_pod_layouts():

@@ -300,9 +300,38 @@ def test_parallel_packetizer_equals_sequential_oracle(O):
                                                 capi.ptr(K), 1.0, C.byref(cur), lim, capi.ptr(out), len(out), C.byref(n)))
             got.append(out[:n.value].copy())
         assert np.concatenate(got).tobytes() == want.tobytes(), limits
-    # output capacity smaller than the list: exactly max_packets packets, the same ones
+    # output capacity smaller than the list: exactly max_packets packets, the same ones, and the call reports that
+    # the list was cut short instead of returning EMVS_OK with a silently truncated packet list
     out = np.zeros(1000, capi.PACKET_DTYPE)
     n = C.c_size_t(0)
-    capi.check(lib.emvs_packetize(capi.ptr(ev), len(ev), capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam), capi.ptr(K), 1.0,
-                                  capi.ptr(out), 1000, C.byref(n)))
+    rc = lib.emvs_packetize(capi.ptr(ev), len(ev), capi.ptr(tr), len(tr), capi.ptr(I), C.byref(cam), capi.ptr(K), 1.0,
+                            capi.ptr(out), 1000, C.byref(n))
+    assert rc == capi.EMVS_ERR_INVALID and b"max_packets is too small" in lib.emvs_last_error()
     assert n.value == 1000 and out.tobytes() == want[:1000].tobytes()
+
+
+def test_soa_packetizer_equals_aos(O, small_case):
+    """emvs_packetize_soa (timestamps from an int64 nanosecond array, emvs_events_soa) produces the very packets of
+    emvs_packetize on the dvs_msgs::Event structs with the same timestamps — and therefore the oracle's."""
+    lib = capi.load()
+    ev = small_case.events[0]
+    cam = small_case.cams[0]
+    tr = np.ascontiguousarray(small_case.trajs[0], capi.STAMPED_POSE_DTYPE)
+    virt = small_case.virts[0]
+    soa = api.EventsSoA.from_events(ev)
+    assert len(soa) == len(ev) and soa.nbytes_device == 4 * len(ev)
+    es = soa.c_struct()
+    cs = cam.c_struct()
+    out = np.zeros(len(ev) // 1024 + 1, capi.PACKET_DTYPE)
+    n = C.c_size_t(0)
+    capi.check(lib.emvs_packetize_soa(C.byref(es), capi.ptr(tr), len(tr), capi.ptr(np.ascontiguousarray(small_case.T_rv_w)),
+                                      C.byref(cs), capi.ptr(virt), float(small_case.depths[0]), capi.ptr(out), len(out),
+                                      C.byref(n)))
+    assert out[:n.value].tobytes() == small_case.packets[0].tobytes()
+    # too few events / missing arrays are errors, not crashes
+    short = api.EventsSoA(soa.x[:100], soa.y[:100], soa.t_ns[:100]).c_struct()
+    assert lib.emvs_packetize_soa(C.byref(short), capi.ptr(tr), len(tr), capi.ptr(np.ascontiguousarray(small_case.T_rv_w)),
+                                  C.byref(cs), capi.ptr(virt), 1.0, capi.ptr(out), len(out), C.byref(n)) == capi.EMVS_ERR_TOO_FEW
+    bad = capi.EventsSoA(None, soa.y.ctypes.data, soa.t_ns.ctypes.data, len(soa))
+    assert lib.emvs_packetize_soa(C.byref(bad), capi.ptr(tr), len(tr), capi.ptr(np.ascontiguousarray(small_case.T_rv_w)),
+                                  C.byref(cs), capi.ptr(virt), 1.0, capi.ptr(out), len(out), C.byref(n)) == capi.EMVS_ERR_INVALID
