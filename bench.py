@@ -1,32 +1,39 @@
 #!/usr/bin/env python
 """bench.py — the driver's benchmark contract for the DSI ray-voting path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
 
 One "step" = one pass of the hot path over one batch of synthetic input (BASELINE.json
 configs[1]: DSEC-like stereo pair, 5 M events per camera, 640x480x256 DSI, harmonic fusion):
 
     for each camera: event warp + resetGrid + fillVoxelGrid        (MapperEMVS::evaluateDSI)
-    [N > 1: one NCCL allreduce(sum) of each camera's partial DSI]
+    [N > 1: sum of the ranks' partial DSIs (NVLink peer reduce under the votes, or ncclAllReduce)]
     harmonic-mean fusion + Z-argmax + index->depth                 (process_1 step 2-3)
 
 Metric (BASELINE.json): Mevents/s = events of all cameras of all ranks / step time; the depth-map
 milliseconds (fuse + argmax) and the build-only Mevents/s are reported beside it.
 
-  value  inputs (events, packets) already resident in HBM, timed with CUDA events on the
-         engine's stream, max over ranks.
-  e2e    the reference-facing call sequence (MapperEMVS.evaluateDSI per camera with HOST event
-         buffers in pinned memory -> fuse_collapse into HOST maps): host packet stage, H2D of
-         the events, build, fuse/argmax, D2H of depth/confidence/index all inside the timed region.
+  value          inputs (events, packets) already resident in HBM, timed with CUDA events on the
+                 engine's stream, max over ranks.
+  e2e            the reference's own call sequence (MapperEMVS.evaluateDSI per camera with HOST
+                 dvs_msgs::Event buffers in pinned memory -> fuse_collapse into HOST maps): host packet stage,
+                 H2D of the events, build, fuse/argmax, D2H of depth/confidence/index all inside the timed
+                 region, all `steps` timed.  No call the reference does not have.
+  e2e_streaming  the same with the next step's first list announced by emvs_mapper_prefetch_dsi (a streaming
+                 caller: its upload and packet stage run under the current votes).
+  e2e_soa        e2e_streaming with structure-of-arrays event lists (x, y, t separate: 4 bytes per event cross
+                 PCIe instead of 16).
+  parity         the maps / counts / checksums of the timed configuration against the CPU oracle (N = 1) and
+                 against an unsharded build on rank 0 (N > 1); outside every timed region.
 
-Multi-GPU (weak scaling): every rank owns one packet-aligned sub-interval of EVERY camera's event
-stream (5 M events/camera/rank), builds partial DSIs; each Z-slab is summed over the ranks with
-ncclAllReduce as soon as it is voted (overlapped with the next slab's votes), then every rank
-fuses + collapses (replicated).  Launched by torchrun; torch.distributed is only the
-rendezvous / barrier plumbing.
+Multi-GPU: every rank owns one packet-aligned sub-interval of EVERY camera's event stream.
+  --scaling weak   (default) 5 M events/camera/GPU — the stream gets denser with N;
+  --scaling strong --events-per-cam E: E events/camera in total, split over the N GPUs (BASELINE.json configs[3] is
+                   E = 20 M on 8 GPUs).
+Launched by torchrun; torch.distributed is only the rendezvous / barrier plumbing.
 
 `--impl reference` times the CPU oracle (the restated reference loops, oracle/) on a bounded
-sample of the same workload with all host threads; it never touches the GPU.
+sample of the same workload with all host threads; it never touches the GPU or libemvs_b200.so.
 """
 import argparse
 import json
@@ -56,14 +63,15 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dsec_stereo", choices=["dsec_stereo", "bar4"],
                     help="dsec_stereo = BASELINE.json configs[1] (the metric's configuration); bar4 = configs[2]")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --events-per-cam events per camera PER GPU; strong: in total, split over the GPUs")
     ap.add_argument("--events-per-cam", type=int, default=0, help="default: 5 M (dsec_stereo), 10 M (bar4)")
     ap.add_argument("--kind", default="structured", choices=["structured", "uniform"])
     ap.add_argument("--cpu-sample-events", type=int, default=5_000_000,
                     help="events per camera of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-prefetch", action="store_true",
-                    help="e2e without emvs_context_prefetch_events (every step then waits for its first upload)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU DSI exchange: fused reduce+fuse+argmax over NVLink peer memory, or "
                          "slab-wise ncclAllReduce overlapped with voting followed by a local sweep")
@@ -84,17 +92,27 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def config_block(args, n_cams, dims, method, world):
+    """The keys that name the workload — identical in the B200 arm and in the reference arm, so the driver can see
+    that both lines are about the same configuration."""
+    return {"workload": WORKLOAD, "cameras": n_cams, "dsi": [int(d) for d in dims], "fusion": FUSION_NAMES[method],
+            "event_distribution": args.kind, "scaling": args.scaling, "gpus": world,
+            "events_per_camera": int(args.events_per_cam * (world if args.scaling == "weak" else 1)),
+            "events_per_camera_per_gpu": (int(args.events_per_cam) if args.scaling == "weak"
+                                          else int(args.events_per_cam // world)),
+            "l2": "inputs + DSIs (> 700 MB per step) exceed the 126 MB L2; no explicit flush"}
+
+
 # ----------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------
-def make_workload(n_events, rank, kind):
-    """Seeded synthetic stereo streams.  Every rank sees the same scene, rig and trajectory and
-    owns shard `rank` of each camera's event stream (an independent sample of the window) — weak
-    scaling: the per-GPU event count is fixed."""
+def make_workload(n_events, stream, kind):
+    """Seeded synthetic stereo streams.  `stream` selects an independent event sample of the same scene, rig and
+    trajectory (weak scaling: rank r owns sample r of a denser stream, the per-GPU event count is fixed)."""
     from dvs_mcemvs_b200 import synth
     sc, _, method, desc = synth.config(WORKLOAD, events_per_cam=n_events)
     cams = sc.rig.cams
-    events = [sc.events(i, n_events, kind, stream=rank) for i in range(len(cams))]
+    events = [sc.events(i, n_events, kind, stream=stream) for i in range(len(cams))]
     trajs = [sc.trajectory(i) for i in range(len(cams))]
     return sc, cams, events, trajs, sc.T_rv_w(), method, desc
 
@@ -154,10 +172,11 @@ class ClockSampler:
 _CPU_WORKLOAD = {}
 
 
-def cpu_reference(args, n_full):
+def cpu_reference(args, n_full, keep=False):
     """Times the restated reference loops on `--cpu-sample-events` events per camera (the vote
     loop is linear in the event count; fusion and argmax do not depend on it) and converts to the
-    full workload: t_full = t_build * n_full / n_sample + t_fuse + t_argmax."""
+    full workload: t_full = t_build * n_full / n_sample + t_fuse + t_argmax.
+    keep=True also returns what the run computed (volumes, counts, maps) for the parity block."""
     from oracle import oracle as O
     O.use_all_host_threads()   # torchrun sets OMP_NUM_THREADS=1 for its workers; the baseline gets every host thread
     n_s = min(args.cpu_sample_events, n_full)
@@ -167,69 +186,81 @@ def cpu_reference(args, n_full):
     sh = sc.shape
     dimX, dimY, dimZ = cams[0].width, cams[0].height, sh.dimZ_
     depths = O.depth_vector(sh.min_depth_, sh.max_depth_, dimZ, sh.inverse_depth)
-    t_build, vols, n_voted = 0.0, [], 0
+    t_build, vols, counts = 0.0, [], []
     for cam, ev, tr in zip(cams, events, trajs):
         virt = O.virtual_camera(cam.fx, cam.cx, cam.cy, dimX, sh.fov_)
         t0 = time.perf_counter()
         pk = O.packetize(ev, tr, T_rv_w, np.array([cam.fx, cam.fy, cam.cx, cam.cy], np.float32), virt, depths[0])
-        dsi, _ = O.build_dsi(ev, pk, cam.lut, cam.width, depths, virt, dimX, dimY)
+        dsi, inb = O.build_dsi(ev, pk, cam.lut, cam.width, depths, virt, dimX, dimY)
         t_build += time.perf_counter() - t0
         vols.append(dsi)
-        n_voted += len(pk) * 1024
+        counts.append(inb)
+    n_cams = len(cams)
     t0 = time.perf_counter()
-    fused = O.fuse_reference(method, vols, copy_arg=True)   # by-value argument copy like the reference
+    if n_cams <= 3:
+        fused = O.fuse_reference(method, vols, copy_arg=True)   # by-value argument copy like the reference
+    else:
+        fused = O.fuse_nary(method, vols)                       # > 3 cameras: the n-ary extension
     t_fuse = time.perf_counter() - t0
     t0 = time.perf_counter()
-    O.collapse_max(fused, depths)
+    conf, idx, depth = O.collapse_max(fused, depths)
     t_argmax = time.perf_counter() - t0
     t_full = t_build * (n_full / n_s) + t_fuse + t_argmax
-    n_cams = len(cams)
     ref_code = None
     try:   # the reference's OWN Grid3D code (compiled in place into oracle/_ref) for the fusion + argmax stage
         from oracle import ref as R
-        if R.available():
+        if R.available() and n_cams == 2:
             f_ms, a_ms, conf_r, _ = R.time_fuse_collapse(vols[0], vols[1], method)
             ref_code = {"fuse_ms": f_ms, "argmax_ms": a_ms, "depth_map_ms": f_ms + a_ms,
                         "what": "cartesian3dgrid.h fusion ops (by-value argument, .at()) + Grid3D::collapseMaxZSlice compiled "
                                 "from the reference sources (oracle/_ref); the build stage has no compilable reference"}
     except Exception as e:   # never let the extra baseline break the bench line
         ref_code = {"unavailable": str(e)[:200]}
-    return {
+    block = {
         "value": n_cams * n_full / t_full / 1e6, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-        "sample": (f"{n_s} events/camera x {n_cams} cameras voted into the full 640x480x256 DSI by the oracle "
+        "sample": (f"{n_s} events/camera x {n_cams} cameras voted into the full {dimX}x{dimY}x{dimZ} DSI by the oracle "
                    f"(g++ -O3 -fopenmp, OMP over planes like mapper_emvs_stereo.cpp:168), fusion (single thread, "
                    f"by-value copy) and argmax at full size"
                    + ("" if n_s == n_full else f"; build time scaled x{n_full / n_s:.1f} to {n_full} events/camera")),
         "build_mevents_per_s": n_cams * n_s / t_build / 1e6,
         "depth_map_ms": (t_fuse + t_argmax) * 1e3, "fuse_ms": t_fuse * 1e3, "argmax_ms": t_argmax * 1e3,
         "sample_build_s": t_build, "host_cpus": os.cpu_count(), "reference_code_depth_map": ref_code,
-    }, t_full
+    }
+    art = None
+    if keep and n_s == n_full:
+        art = {"vols": vols, "counts": counts, "fused": fused, "conf": conf, "idx": idx, "depth": depth,
+               "mean_square": [O.mean_square(v) for v in vols]}
+    return block, t_full, art
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_full = args.events_per_cam
+    from dvs_mcemvs_b200 import synth
+    synth.LUT_BACKEND = "cv2"      # the DSEC rectification LUT from OpenCV: this arm never maps libemvs_b200.so
+    world = max(1, args.gpus)
+    # the arm's workload is the B200 arm's at the same N: `events_per_camera` of config_block
+    n_full = args.events_per_cam * (world if args.scaling == "weak" else 1)
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        base, t_full = cpu_reference(args, n_full)
+        base, t_full, _ = cpu_reference(args, n_full)
         if i >= args.warmup:
             vals.append(t_full)
         last = base
         if i >= args.warmup and sum(vals) > 240:   # keep the whole run within a few minutes
             break
     t = float(np.mean(vals))
-    n_cams = len(_CPU_WORKLOAD[next(iter(_CPU_WORKLOAD))][1])
-    method = _CPU_WORKLOAD[next(iter(_CPU_WORKLOAD))][5]
+    wl = _CPU_WORKLOAD[next(iter(_CPU_WORKLOAD))]
+    cams, method = wl[1], wl[5]
+    n_cams = len(cams)
     value = n_cams * n_full / t / 1e6
     last["value"] = value
     _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "events_per_camera": n_full, "cameras": n_cams, "dsi": [640, 480, 256],
-                   "fusion": FUSION_NAMES[method], "event_distribution": args.kind},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(args, n_cams, (cams[0].width, cams[0].height, wl[0].shape.dimZ_), method, world),
         "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -243,7 +274,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from dvs_mcemvs_b200 import _capi as capi
-    from dvs_mcemvs_b200 import api
+    from dvs_mcemvs_b200 import api, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -268,18 +299,38 @@ def run_b200(args):
         dist.broadcast(idt, 0)
         ctx.comm_init(idt.cpu().numpy().tobytes(), world, rank)
 
+    strong = args.scaling == "strong" and world > 1
     n_ev = args.events_per_cam
-    sc, cams, events, trajs, T_rv_w, method, desc = make_workload(n_ev, rank, args.kind)
+    # weak: rank r owns sample r of the stream; strong: every rank sees the same list and builds its packet range
+    sc, cams, events_all, trajs, T_rv_w, method, desc = make_workload(n_ev, 0 if strong else rank, args.kind)
     n_cams = len(cams)
     mappers = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
     ltrajs = [api.LinearTrajectory(t) for t in trajs]
     depths = mappers[0].raw_depths_vec_
     dimX, dimY, dimZ = mappers[0].dsi_.size_
 
+    packets_all = [m.packetize(ev, tr, T_rv_w) for m, ev, tr in zip(mappers, events_all, ltrajs)]
+    if strong:
+        # this rank's packet range of every camera; only the events those packets reference are kept (rebased)
+        events, packets = [], []
+        for cam, lo, hi in shard.plan([len(p) for p in packets_all], world, rank):
+            pk = packets_all[cam][lo:hi].copy()
+            if len(pk):
+                e_lo = int(pk["first_event"][0])
+                # one event past the last packet: the packet loop's strict '<' (mapper_emvs_stereo.cpp:88) needs it to
+                # form that packet when this slice is packetised on its own (the e2e leg)
+                e_hi = min(len(events_all[cam]), int(pk["first_event"][-1]) + capi.PACKET_SIZE + 1)
+                pk["first_event"] -= e_lo
+                events.append(np.ascontiguousarray(events_all[cam][e_lo:e_hi]))
+            else:
+                events.append(events_all[cam][:0].copy())
+            packets.append(pk)
+    else:
+        events, packets = events_all, packets_all
+
     # ---- device-resident inputs for `value` -------------------------------------------------
-    packets = [m.packetize(ev, tr, T_rv_w) for m, ev, tr in zip(mappers, events, ltrajs)]
-    d_events = [torch.from_numpy(ev.view(np.uint8).reshape(-1)).cuda() for ev in events]
-    d_packets = [torch.from_numpy(pk.view(np.uint8).reshape(-1)).cuda() for pk in packets]
+    d_events = [torch.from_numpy(ev.view(np.uint8).reshape(-1).copy()).cuda() for ev in events]
+    d_packets = [torch.from_numpy(pk.view(np.uint8).reshape(-1).copy()).cuda() for pk in packets]
     torch.cuda.synchronize()
     d_conf = torch.empty(dimY * dimX, dtype=torch.float32, device="cuda")
     d_depth = torch.empty(dimY * dimX, dtype=torch.float32, device="cuda")
@@ -299,12 +350,15 @@ def run_b200(args):
             return out
         peer = api.PeerExchange(ctx, grids, world, rank, allgather)
 
-    def step_device():
-        if peer is not None:
-            peer.begin()      # slab-wise band reduce over NVLink, overlapped with voting
+    def builds_device():
         for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
             m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None,
                            peer_reduce=peer is not None)
+
+    def step_device():
+        if peer is not None:
+            peer.begin()      # slab-wise band reduce over NVLink, overlapped with voting
+        builds_device()
         if peer is not None:
             peer.fuse_collapse(method, d_tab)
         else:
@@ -313,7 +367,7 @@ def run_b200(args):
     t_all, t_build, t_depth = ctx.timer(), ctx.timer(), ctx.timer()
 
     def timed_device(k):
-        """K steps bracketed by barrier + synchronize; returns (ms total, build ms, depth-map ms)."""
+        """K steps bracketed by barrier + synchronize; returns the total ms."""
         barrier()
         t_all.start()
         for _ in range(k):
@@ -343,57 +397,81 @@ def run_b200(args):
     if peer is not None:
         peer.begin()
     t_build.start()
-    for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
-        m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None,
-                       peer_reduce=peer is not None)
+    builds_device()
     t_build.stop()
     t_depth.start()
     if peer is not None:
-        peer.fuse_collapse(method, d_tab)    # reduce over NVLink + fuse + argmax in one sweep (+ the epoch waits)
+        peer.fuse_collapse(method, d_tab)    # fuse + argmax of this rank's band + distribution of the maps (+ the epoch waits)
     else:
         collapse_device()
     t_depth.stop()
     ctx.sync()
     build_ms, depth_ms = t_build.elapsed_ms(), t_depth.elapsed_ms()
-    votes = int(sum(int(m.counts().sum()) for m in mappers))   # accepted (event, plane) votes of one step
+    counts_local = [m.counts() for m in mappers]       # accepted (event, plane) votes of this rank's shard (peer mode)
+    votes = int(sum(int(c.sum()) for c in counts_local))
     n_voted_events = sum(len(pk) for pk in packets) * capi.PACKET_SIZE
+    if peer is not None:
+        maps_dev = peer.download()                     # the exchanged maps of the timed configuration (every rank has them)
+    else:
+        maps_dev = api.fuse_collapse(grids, method, depths)
+    mean_square = [g.computeMeanSquare() for g in grids] if world == 1 or peer is None else None
 
     # ---- e2e: host buffers through the reference-facing calls ---------------------------------
-    e2e = None
+    e2e_runs = {}
     if not args.no_e2e:
         h_events = []
         for ev in events:
             buf = api.pinned_empty(ev.shape, ev.dtype)
             buf[...] = ev
             h_events.append(buf)
+        h_soa = [api.EventsSoA.from_events(ev, pinned=True) for ev in events]
+        if strong:   # the slice of a rank, packetised on its own, must give that rank's packets of the global list
+            for m, ev, tr, pk in zip(mappers, h_events, ltrajs, packets):
+                mine = m.packetize(ev, tr, T_rv_w)
+                assert mine is not None and mine.tobytes() == pk.tobytes(), "sub-interval packets differ from the global packet list"
 
-        def step_host():
+        def step_host(lists, prefetch):
             if peer is not None:
                 peer.begin()
-            for m, ev, tr in zip(mappers, h_events, ltrajs):
+            for m, ev, tr in zip(mappers, lists, ltrajs):
                 assert m.evaluateDSI(ev, tr, T_rv_w, allreduce=world > 1 and peer is None, peer_reduce=peer is not None)
-            if not args.no_prefetch:
+            if prefetch:
                 # streaming caller: the NEXT step's first event list starts crossing PCIe now, under this step's
                 # votes (every step still uploads every list once, inside the timed region)
-                mappers[0].prefetch(h_events[0], ltrajs[0], T_rv_w)
+                mappers[0].prefetch(lists[0], ltrajs[0], T_rv_w)
             if peer is not None:
                 peer.fuse_collapse(method, d_tab)
                 return peer.download()
             return api.fuse_collapse([m.dsi_ for m in mappers], method, depths)
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_host()
-        k_e2e = max(1, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            conf, idx, depth = step_host()
-        ctx.sync()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / k_e2e
-        h2d = sum(ev.nbytes for ev in events) + sum(pk.nbytes for pk in packets) + depths.nbytes
-        d2h = conf.nbytes + idx.nbytes + depth.nbytes
-        e2e = (e2e_s, h2d, d2h)
+        def time_host(lists, prefetch, bytes_per_event):
+            for _ in range(max(1, min(args.warmup, 2))):
+                step_host(lists, prefetch)
+            ctx.prefetch_cancel()
+            if prefetch:
+                mappers[0].prefetch(lists[0], ltrajs[0], T_rv_w)    # what the previous window's step would have announced
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                conf, idx, depth = step_host(lists, prefetch)
+            ctx.sync()
+            barrier()
+            e2e_s = (time.perf_counter() - t0) / args.steps
+            ctx.prefetch_cancel()
+            h2d = sum(len(ev) for ev in events) * bytes_per_event + sum(pk.nbytes for pk in packets) + depths.nbytes
+            d2h = conf.nbytes + idx.nbytes + depth.nbytes
+            return e2e_s, h2d, d2h, (conf, idx, depth)
+
+        e2e_runs["e2e"] = time_host(h_events, False, 16)
+        e2e_runs["e2e_streaming"] = time_host(h_events, True, 16)
+        e2e_runs["e2e_soa"] = time_host(h_soa, True, 4)
+
+    # ---- parity (outside every timed region) ---------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv_w, packets_all, events_all, events,
+                              packets, method, depths, maps_dev, counts_local, mean_square, strong, peer,
+                              {k: v[3] for k, v in e2e_runs.items()})
 
     # ---- reduce over ranks ------------------------------------------------------------------
     def max_over_ranks(x):
@@ -412,61 +490,62 @@ def run_b200(args):
 
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
-    total_events = sum_over_ranks(float(n_cams * n_ev))
+    total_events = float(n_cams * n_ev) if strong else sum_over_ranks(float(n_cams * n_ev))
     value = total_events / (ms_step * 1e-3) / 1e6
-    if e2e is not None:
-        e2e_s = max_over_ranks(e2e[0])
-        e2e = {"value": total_events / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(e2e[1]),
-               "d2h_bytes_per_step": int(e2e[2]), "ms_per_step": e2e_s * 1e3,
-               "timer": "host wall clock around the blocking public calls (each call syncs its stream)",
-               "prefetch": ("off" if args.no_prefetch else
-                            "the next step's first evaluateDSI is announced with emvs_mapper_prefetch_dsi after the last "
-                            "evaluateDSI of a step (its upload and host packet stage run under the current votes); every "
-                            "list is uploaded and packetised once per step inside the timed region")}
+    votes_all = sum_over_ranks(float(votes))
+    vote_ms_max = max_over_ranks(vote_ms)
+    build_ms, depth_ms = max_over_ranks(build_ms), max_over_ranks(depth_ms)
+    e2e_out = {}
+    notes = {
+        "e2e": "the reference's own call sequence, nothing else: evaluateDSI per camera on pinned dvs_msgs::Event lists, "
+               "fuse_collapse into host maps",
+        "e2e_streaming": "+ the next step's first evaluateDSI is announced with emvs_mapper_prefetch_dsi after the last "
+                         "evaluateDSI of a step (its upload and host packet stage run under the current votes); every list "
+                         "is uploaded and packetised once per step inside the timed region",
+        "e2e_soa": "e2e_streaming with structure-of-arrays event lists (emvs_mapper_evaluate_dsi_soa): x, y cross PCIe, "
+                   "timestamps stay on the host",
+    }
+    for name, (e2e_s, h2d, d2h, _) in e2e_runs.items():
+        e2e_s = max_over_ranks(e2e_s)
+        e2e_out[name] = {"value": total_events / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": args.steps,
+                         "timer": "host wall clock around the blocking public calls (each call syncs its stream), max over ranks",
+                         "calls": notes[name]}
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # roofline of the dominant kernel (k_vote): algorithmic bytes = 32 B per accepted vote
-        # (4 voxels x (4 B read + 4 B write)) + 8 B per warped event read.
-        alg_bytes_step = votes * 32.0 + n_voted_events * 8.0
-        vote_ms_per_step = vote_ms / args.steps
-        launches_per_step = vote_launches / args.steps
-        achieved = alg_bytes_step / (vote_ms_per_step * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_vote_grouped", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": load_ncu_traffic(),
-                "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
-                "avg_launch_ms": vote_ms_per_step / launches_per_step, "launches_per_step": launches_per_step,
-                "kernel_share_of_step": vote_ms_per_step / ms_step,
-                "physical_bound": {"what": "RED sectors retired by the L1/L2 path: one 16-byte red.global.add.v4.f32 per vote, the "
-                                           "quads of 8 consecutive planes interleaved so that the 8 lanes voting one event share lines",
-                                   "red_payload_tb_per_s": votes * 16.0 / (vote_ms_per_step * 1e-3) / 1e12,
-                                   "min_gsectors_per_s": votes * 0.5 / (vote_ms_per_step * 1e-3) / 1e9,
-                                   "microbench_ceiling_gsectors_per_s": 185.0,
-                                   "source": "profiles/r1_red_microbench.csv (random 16-byte REDs, L2-resident footprint); "
-                                             "min_gsectors assumes every 32-byte sector receives two votes"},
-                "note": "uncached-scatter model: votes resolve as red.global.add.v4.f32 in an L2-resident slab, so "
-                        "a fraction above what DRAM counters show is cache-served, see DESIGN.md §4"}
+        roof = roofline_block(peak, peak_src, votes, n_voted_events, vote_ms / args.steps, vote_launches / args.steps, ms_step,
+                              n_cams, n_ev if not strong else sum(len(e) for e in events) // max(n_cams, 1), dimX, dimY, dimZ)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "description": desc, "events_per_camera_per_gpu": n_ev, "cameras": n_cams,
-                       "dsi": [dimX, dimY, dimZ], "fusion": FUSION_NAMES[method], "event_distribution": args.kind,
-                       "sharding": ("none" if world == 1 else
-                                    "event sub-interval per GPU; slab-wise reduce of each GPU's row band over NVLink peer memory under the votes, then fuse+argmax of the band and peer stores of the maps"
-                                    if peer is not None else
-                                    "event sub-interval per GPU; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting"),
-                       "l2": "inputs+DSIs (>700 MB/step) exceed the 126 MB L2; no explicit flush"},
-            "build_mevents_per_s": n_cams * n_ev / (build_ms * 1e-3) / 1e6, "build_ms": build_ms,
-            "depth_map_ms": depth_ms, "accepted_votes_per_step": votes,
-            "stage_note": ("build_ms = event stage + reset + votes + merges of both cameras; depth_map_ms = fuse + argmax + index->depth"
+            "config": config_block(args, n_cams, (dimX, dimY, dimZ), method, world),
+            "config_detail": {"description": desc,
+                              "sharding": ("none" if world == 1 else
+                                           "event sub-interval per GPU; slab-wise reduce of each GPU's row band over NVLink peer memory under the votes, then fuse+argmax of the band and peer stores of the maps"
+                                           if peer is not None else
+                                           "event sub-interval per GPU; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting")},
+            "build_mevents_per_s": total_events / (build_ms * 1e-3) / 1e6, "build_ms": build_ms,
+            "depth_map_ms": depth_ms, "accepted_votes_per_step": int(votes_all),
+            "vote_ms_per_launch_max_over_ranks": vote_ms_max / max(vote_launches, 1),
+            "stage_note": ("build_ms = event stage + reset + votes + merges of all cameras; depth_map_ms = fuse + argmax + index->depth"
                            + ("" if world == 1 else
                               " of this GPU's row band + distribution of the maps; the slab-wise peer reduce runs inside build_ms" if peer is not None else
                               "; the slab-wise ncclAllReduce runs inside build_ms, overlapped with voting")),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(n_launch), "roofline": roof,
+            "mean_square": mean_square,
+            "clocks": clocks, "e2e": e2e_out.get("e2e"), "e2e_streaming": e2e_out.get("e2e_streaming"),
+            "e2e_soa": e2e_out.get("e2e_soa"), "gpu_launches": int(n_launch), "roofline": roof, "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"], _ = cpu_reference(args, n_ev)
+            cb = parity.get("_cpu_baseline") if parity else None
+            if cb is None:
+                _CPU_WORKLOAD.setdefault((min(args.cpu_sample_events, n_ev), args.kind),
+                                         (sc, cams, events_all, trajs, T_rv_w, method, desc))
+                cb, _, _ = cpu_reference(args, n_ev)
+            out["cpu_baseline"] = cb
+        if parity:
+            parity.pop("_cpu_baseline", None)
         _emit(json.dumps(out))
     if world > 1:
         if peer is not None:
@@ -477,12 +556,136 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def load_ncu_traffic():
-    """dram bytes per k_vote launch from the committed ncu capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "vote_traffic.json")
+def parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv_w, packets_all, events_all, events, packets,
+                 method, depths, maps_dev, counts_local, mean_square, strong, peer, e2e_maps):
+    """N = 1: the timed configuration's counts / maps / checksums against the CPU oracle on the same events (the run
+    that is also the cpu_baseline).  N > 1: the exchanged maps and the summed counts against an UNSHARDED build of all
+    ranks' events on rank 0's GPU (itself oracle-checked at N = 1).  Returns a dict on rank 0, None elsewhere."""
+    from oracle import parity as P
+    conf, idx, depth = maps_dev
+    if world == 1:
+        n_ev = args.events_per_cam
+        if min(args.cpu_sample_events, n_ev) != n_ev:
+            return {"skipped": "the CPU sample is smaller than the workload (--cpu-sample-events): no full-size oracle run"}
+        _CPU_WORKLOAD[(n_ev, args.kind)] = (sc, cams, events_all, trajs, T_rv_w, method, "")
+        cb, _, art = cpu_reference(args, n_ev, keep=True)
+        p = P.compare_maps(conf, idx, depth, art["conf"], art["idx"], art["depth"], art["fused"])
+        p["counts_exact"] = bool(all(np.array_equal(c, o) for c, o in zip(counts_local, art["counts"])))
+        p["mean_square_gpu"] = mean_square
+        p["mean_square_oracle"] = art["mean_square"]
+        p["mean_square_rel"] = float(max(abs(g - o) / max(abs(o), 1e-300) for g, o in zip(mean_square, art["mean_square"])))
+        for name, (c2, i2, d2) in e2e_maps.items():   # the e2e legs (host buffers, split upload, prefetch, SoA) produce the same maps
+            q = P.compare_maps(c2, i2, d2, art["conf"], art["idx"], art["depth"], art["fused"])
+            p[name + "_ok"] = P.verdict(q)
+        p["against"] = "CPU oracle (oracle/emvs_oracle.cpp) on the same events, full size, all planes"
+        p["ok"] = P.verdict(p) and all(p.get(k + "_ok", True) for k in e2e_maps)
+        p["_cpu_baseline"] = cb
+        return p
+    # ---- N > 1 ------------------------------------------------------------------------------
+    dimZ = len(depths)
+    cnt = torch.from_numpy(np.stack(counts_local).astype(np.int64)).cuda()
+    if peer is not None:
+        dist.all_reduce(cnt)          # peer mode keeps per-rank counts: the job's counts are their sum
+    cnt = cnt.cpu().numpy().astype(np.uint64)
+    full = None
+    if strong:
+        if rank == 0:
+            full = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
+            for m, ev, pk in zip(full, events_all, packets_all):
+                m.build(ev, pk)
+    else:
+        # weak scaling: rank 0 accumulates every rank's stream into one DSI per camera (votes add)
+        for cam in range(len(cams)):
+            ev_t = torch.from_numpy(events[cam].view(np.uint8).reshape(-1).copy()).cuda()
+            pk_n = torch.tensor([len(packets[cam])], dtype=torch.int64, device="cuda")
+            sizes = [torch.zeros_like(pk_n) for _ in range(world)]
+            dist.all_gather(sizes, pk_n)
+            max_pk = int(max(int(s.item()) for s in sizes))
+            pk_pad = np.zeros(max_pk, packets[cam].dtype)
+            pk_pad[:len(packets[cam])] = packets[cam]
+            pk_t = torch.from_numpy(pk_pad.view(np.uint8).reshape(-1).copy()).cuda()
+            ev_list = [torch.empty_like(ev_t) for _ in range(world)] if rank == 0 else None
+            pk_list = [torch.empty_like(pk_t) for _ in range(world)] if rank == 0 else None
+            dist.gather(ev_t, ev_list, dst=0)
+            dist.gather(pk_t, pk_list, dst=0)
+            torch.cuda.synchronize()     # the engine reads these tensors on its own stream
+            if rank == 0:
+                if full is None:
+                    full = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
+                for r in range(world):
+                    full[cam].build_device(ev_list[r].data_ptr(), len(events[cam]), pk_list[r].data_ptr(), int(sizes[r].item()),
+                                           accumulate=r > 0)
+                ctx.sync()
+            del ev_list, pk_list
+    p = None
+    if rank == 0:
+        conf_f, idx_f, depth_f = api.fuse_collapse([m.dsi_ for m in full], method, depths)
+        fused_g = api.Grid3D(ctx, *full[0].dsi_.size_)
+        api.fuse_collapse([m.dsi_ for m in full], method, depths, fused_out=fused_g)
+        p = P.compare_maps(conf, idx, depth, conf_f, idx_f, depth_f, fused_g.download())
+        fused_g.close()
+        p["counts_exact"] = bool(all(np.array_equal(cnt[i], full[i].counts()) for i in range(len(cams))))
+        for name, (c2, i2, d2) in e2e_maps.items():
+            q = P.compare_maps(c2, i2, d2, conf_f, idx_f, depth_f)
+            q["idx_mismatches_are_near_ties"] = None
+            p[name + "_ok"] = P.verdict(q)
+        p["against"] = ("an unsharded build of all ranks' events on rank 0's GPU (that single-GPU path is what the N = 1 "
+                        "bench line and tests/test_gpu_fullsize.py check against the CPU oracle)")
+        p["ok"] = P.verdict(p) and all(p.get(k + "_ok", True) for k in e2e_maps)
+        for m in full:
+            m.close()
+    # every rank holds identical maps
+    t = torch.from_numpy(np.ascontiguousarray(conf).copy()).cuda()
+    ref = t.clone()
+    dist.broadcast(ref, 0)
+    same = torch.tensor([1 if torch.equal(t, ref) else 0], device="cuda")
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        p["maps_identical_on_all_ranks"] = bool(same.item())
+        p["ok"] = bool(p["ok"] and same.item())
+    return p
+
+
+def roofline_block(peak, peak_src, votes, n_voted_events, vote_ms_per_step, launches_per_step, ms_step, n_cams, n_ev_per_cam,
+                   dimX, dimY, dimZ):
+    """The dominant kernel (k_vote_tma) against what limits it.  SURVEY.md §8(d) defines the algorithmic bytes
+    (32 B per accepted vote: 4 voxels x read + write, + 8 B per warped event); physically every vote is ONE 16-byte
+    red.global.add.v4.f32 that resolves in an L2-resident slab, so DRAM is idle and the limiter is the path that carries
+    RED payload from the SMs into the L2 atomic units.  Both views are printed; `frac` is the physical one."""
+    red = load_json("profiles/red_port_ceiling.json") or {}
+    payload = votes * 16.0 / (vote_ms_per_step * 1e-3) / 1e9            # GB/s of RED payload delivered to L2
+    alg_bytes_step = votes * 32.0 + n_voted_events * 8.0
+    alg = alg_bytes_step / (vote_ms_per_step * 1e-3) / 1e9
+    ceil = red.get("payload_gb_per_s")
+    slab = 16
+    compulsory = n_cams * ((dimX * dimY * dimZ) * 4.0 * 2 + n_ev_per_cam * 16.0 * ((dimZ + slab - 1) // slab))
+    return {
+        "bound": "l2_red_port", "kernel": "k_vote_tma<8>", "achieved": payload, "peak": ceil, "unit": "GB/s",
+        "frac": (payload / ceil) if ceil else None,
+        "peak_source": red.get("source", "profiles/red_port_ceiling.json missing"),
+        "what": "RED payload (16 B per accepted vote) per second delivered by the vote kernel, against the ceiling a "
+                "micro-benchmark reaches with the same access pattern (8 lanes per 128-byte line, full sectors) and no "
+                "arithmetic; port theory: 148 SMs x 32 B/clk x 1.965 GHz = 9307 GB/s",
+        "traffic": (load_json("profiles/vote_traffic.json") or {}).get("dram_bytes_per_launch"),
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per vote launch, ncu --set full (profiles/vote_traffic.json)",
+        "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
+        "avg_launch_ms": vote_ms_per_step / launches_per_step, "launches_per_step": launches_per_step,
+        "kernel_share_of_step": vote_ms_per_step / ms_step,
+        "hbm_algorithmic": {"achieved": alg, "peak": peak, "unit": "GB/s", "frac": alg / peak, "peak_source": peak_src,
+                            "label": "cache-served: SURVEY.md §8(d)'s uncached-scatter bytes (32 B per vote) over the kernel "
+                                     "time; the read-modify-write happens in L2, so this exceeds 1 while DRAM is ~5 % busy"},
+        "compulsory": {"bytes_per_step": compulsory, "time_at_hbm_peak_ms": compulsory / (peak * 1e9) * 1e3,
+                       "frac_of_step": compulsory / (peak * 1e9) * 1e3 / ms_step,
+                       "label": "SURVEY.md §8(d)(ii): Nvox*4*2 + Ne*16*ceil(Nz/slab) per camera — the DRAM traffic a perfect "
+                                "implementation of this slab scheme cannot avoid, as a share of the measured step"},
+    }
+
+
+def load_json(rel):
+    p = os.path.join(ROOT, rel)
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            return json.load(f)
     return None
 
 

@@ -152,6 +152,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if os.environ.get("EMVS_B200_FORBID_LOAD"):   # set by tests to prove that a code path (bench.py's CPU arm) never maps the library
+        raise ImportError("libemvs_b200.so must not be loaded in this process (EMVS_B200_FORBID_LOAD is set)")
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

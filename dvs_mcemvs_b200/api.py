@@ -736,8 +736,7 @@ def process_2_sharded(ctx, cams, trajectories, events, dsi_shape, T_rv_w, stereo
     process_2(num_subintervals=world) (process2.cpp:98-247) with the time loop spread over the ranks; float sums
     differ by the allreduce order only.  Needs ctx.comm_init; every rank returns the same Grid3D.
 
-    NOTE: composed from calls that are each covered by the GPU suite (evaluateDSI, Grid3D ops, Grid3D.allreduce); the
-    composition itself has not been run on a multi-GPU box in round 1."""
+    Checked against process_2 by tests/mgpu_check_alg2.py (torchrun, 2 and 8 ranks)."""
     if stereo_fusion not in _PAIR_METHOD:
         raise ValueError("Improper fusion method selected")
     if temporal_fusion not in (2, 4):

@@ -80,6 +80,23 @@ def rig_esim():
 _DSEC_P = (557.9686136352767, 558.0457356705808, 345.95312896446654, 217.50102178331326)
 
 
+# Who computes the DSEC rectification LUT: "engine" = the library's precomputeRectifiedPoints restatement
+# (emvs_rectify_lut), "cv2" = OpenCV's cv2.undistortPoints, which it equals bit for bit (tests/test_rectify_lut.py).
+# bench.py's CPU reference arm selects "cv2" so that it never maps libemvs_b200.so.
+LUT_BACKEND = "engine"
+
+
+def _plumb_bob_camera(width, height, Km, D, P):
+    if LUT_BACKEND == "cv2":
+        import cv2
+        xs, ys = np.meshgrid(np.arange(width, dtype=np.float32), np.arange(height, dtype=np.float32))
+        px = np.stack([xs, ys], -1).reshape(-1, 1, 2)
+        lut = cv2.undistortPoints(px, np.asarray(Km, np.float64), np.asarray(D, np.float64), R=np.eye(3),
+                                  P=np.asarray(P, np.float64)).reshape(-1, 2)
+        return CameraModel(width, height, P[0][0], P[1][1], P[0][2], P[1][2], lut=lut)
+    return CameraModel.from_camera_info(width, height, Km, D, np.eye(3), P, "plumb_bob")
+
+
 def rig_dsec():
     Ks = [(553.4686750102932, 553.3994078799127, 346.65339162053317, 216.52092103243012),
           (552.1819422959984, 551.4454720096484, 336.87432177064744, 226.32630571403274)]
@@ -91,7 +108,7 @@ def rig_dsec():
     for K, D in zip(Ks, Ds):
         Km = [[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]]
         # the LUT exactly as precomputeRectifiedPoints builds it (image_geometry::rectifyPoint -> cv::undistortPoints)
-        cams.append(CameraModel.from_camera_info(640, 480, Km, D, np.eye(3), P, "plumb_bob"))
+        cams.append(_plumb_bob_camera(640, 480, Km, D, P))
         raw.append((K, D))
     return Rig(cams, [0.0, 0.599], raw)
 

@@ -4,7 +4,7 @@ single-GPU api.process_2 with num_subintervals = world, run under torchrun:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29512 tests/mgpu_check_alg2.py
 
-NOT wired into pytest yet: written in round 1 after the multi-GPU budget was spent; run it first thing in round 2."""
+Run by tests/test_gpu_multi.py::test_two_rank_alg2_sharded_matches_process_2 on boxes with >= 2 GPUs."""
 import os
 import sys
 

@@ -9,8 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_contract_line():
+    # EMVS_B200_FORBID_LOAD: the CPU arm must not map libemvs_b200.so (its DSEC rectification LUT comes from cv2)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--events-per-cam", "60000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--events-per-cam", "60000"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, EMVS_B200_FORBID_LOAD="1"))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -21,6 +23,10 @@ def test_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32" and d["gpu_launches"] == 0
     assert d["config"]["workload"] == "dsec_stereo" and d["config"]["dsi"] == [640, 480, 256] and d["config"]["fusion"] == "harmonic"
+    # the keys both arms print (the driver compares the two `config` dicts)
+    assert sorted(d["config"]) == sorted(["workload", "cameras", "dsi", "fusion", "event_distribution", "scaling", "gpus",
+                                          "events_per_camera", "events_per_camera_per_gpu", "l2"])
+    assert d["config"]["events_per_camera"] == 60000 and d["config"]["gpus"] == 1 and d["scaling"] == "weak"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "Mevents/s" and "sample" in cb and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mevents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

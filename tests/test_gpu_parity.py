@@ -115,8 +115,9 @@ def test_evaluate_dsi_split_upload(ctx, small_case, built_small, percent):
 
 
 def test_prefetch_events(ctx, small_case, built_small):
-    """A list announced with prefetch_events is uploaded ahead of its evaluateDSI, other lists may be built in
-    between, and a replaced / unmatched prefetch falls back to the ordinary upload."""
+    """A list announced with prefetch_events is uploaded ahead of the NEXT evaluateDSI; that call consumes it when it
+    names the same list and drops it otherwise (emvs_b200.h lifetime rule: an announcement never outlives the next
+    host-buffer build, so it cannot be matched to an unrelated later list at the same address)."""
     import time
     _, oracle = built_small
     trs = [api.LinearTrajectory(t) for t in small_case.trajs]
@@ -131,8 +132,10 @@ def test_prefetch_events(ctx, small_case, built_small):
         assert np.array_equal(ms[i].counts(), oracle[i][1])
         np.testing.assert_allclose(ms[i].dsi_.download(), oracle[i][0], rtol=DSI_RTOL, atol=DSI_ATOL)
     try:
+        assert ctx.prefetch_pending() == 0
         ctx.prefetch_events(pinned[0])
-        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)      # an unrelated list in between
+        g1 = ctx.prefetch_pending()
+        assert g1 > 0
         # white box: once the prefetch copy has landed, scribble over the pixel coordinates on the host (timestamps,
         # which the host packet stage reads, stay).  Only the prefetched device copy still holds the real events.
         time.sleep(0.2)
@@ -140,13 +143,33 @@ def test_prefetch_events(ctx, small_case, built_small):
         pinned[0]["x"] = 0
         assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
         pinned[0]["x"] = saved
+        check(0)
+        assert ctx.prefetch_pending() == 0                                   # consumed
+        # an unrelated list in between DROPS the announcement; the announced list is then uploaded the ordinary way
+        ctx.prefetch_events(pinned[0])
+        assert ctx.prefetch_pending() > g1                                   # every prefetch gets a new generation
+        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)
+        assert ctx.prefetch_pending() == 0
+        time.sleep(0.2)
+        half = pinned[0].copy()
+        pinned[0]["x"][::2] = 1                                              # the list changed after the (dropped) prefetch ...
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)       # ... and THIS content is what gets voted
+        changed = ms[0].dsi_.download()
+        pinned[0][...] = half
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
         check(0); check(1)
-        # a second prefetch replaces the first; the replaced list is then uploaded the ordinary way
+        assert not np.allclose(changed, oracle[0][0], rtol=1e-3, atol=1e-3)  # the stale device copy was NOT used
+        # a second prefetch replaces the first
         ctx.prefetch_events(pinned[0])
         ctx.prefetch_events(pinned[1])
-        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
         assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)
-        check(0); check(1)
+        check(1)
+        # cancel: the arrays are the caller's again, the next call uploads what is there now
+        ctx.prefetch_events(pinned[0])
+        ctx.prefetch_cancel()
+        assert ctx.prefetch_pending() == 0
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+        check(0)
         # steady state of a streaming caller: prefetch the next window's first list before collecting this window's maps
         for _ in range(3):
             assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
@@ -159,13 +182,14 @@ def test_prefetch_events(ctx, small_case, built_small):
         with pytest.raises(ValueError):
             ctx.prefetch_events(small_case.events[0][::2])
     finally:
+        ctx.prefetch_cancel()
         for m in ms:
             m.close()
 
 
 def test_prefetch_dsi(ctx, small_case, built_small):
-    """MapperEMVS.prefetch runs the upload and the host packet stage of a later evaluateDSI ahead of time; the later
-    call with the same arguments only launches kernels, any other call falls back."""
+    """MapperEMVS.prefetch runs the upload and the host packet stage of the next evaluateDSI ahead of time; that
+    call with the same arguments only launches kernels, any other call falls back / drops the announcement."""
     import time
     _, oracle = built_small
     trs = [api.LinearTrajectory(t) for t in small_case.trajs]
@@ -182,10 +206,10 @@ def test_prefetch_dsi(ctx, small_case, built_small):
         np.testing.assert_allclose(m.dsi_.download(), oracle[i][0], rtol=DSI_RTOL, atol=DSI_ATOL)
     try:
         # white box: after the prefetch has landed, destroy coordinates AND timestamps on the host; only a call that
-        # uses the prefetched events and the prefetched packets can still produce the right DSI
+        # uses the prefetched events and the prefetched packets can still produce the right DSI.  Builds from
+        # device-resident inputs in between leave the announcement alone.
+        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)
         ms[0].prefetch(pinned[0], trs[0], small_case.T_rv_w)
-        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)      # unrelated builds in between
-        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)      # (twice: both avoid the reserved packet buffer)
         time.sleep(0.2)
         saved = pinned[0].copy()
         pinned[0]["x"] = 0
@@ -197,6 +221,12 @@ def test_prefetch_dsi(ctx, small_case, built_small):
         ms[0].prefetch(pinned[0], trs[0], small_case.T_rv_w)
         assert m0b.evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
         check(m0b, 0)
+        # an unrelated evaluateDSI drops the announcement (and its reserved packet buffer)
+        ms[0].prefetch(pinned[0], trs[0], small_case.T_rv_w)
+        assert ms[1].evaluateDSI(pinned[1], trs[1], small_case.T_rv_w)
+        assert ctx.prefetch_pending() == 0
+        assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
+        check(ms[0], 0); check(ms[1], 1)
         # steady state of a streaming caller
         for _ in range(3):
             assert ms[0].evaluateDSI(pinned[0], trs[0], small_case.T_rv_w)
@@ -210,6 +240,7 @@ def test_prefetch_dsi(ctx, small_case, built_small):
         ms[0].prefetch(pinned[0][:1000].copy(), trs[0], small_case.T_rv_w)
         assert ms[0].evaluateDSI(pinned[0][:1000], trs[0], small_case.T_rv_w) is False
     finally:
+        ctx.prefetch_cancel()
         for m in ms + [m0b]:
             m.close()
 
