@@ -113,6 +113,12 @@ struct emvs_context {
   unsigned int* d_work = nullptr;
   uint32_t vote_ctas_per_sm = 7;
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
+  // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
+  int zero_ctas = 296;                 // EMVS_ZERO_CTAS: grid of the scratch re-zero kernel (0: cudaMemsetAsync)
+  int peer_reduce_ctas = 64;           // EMVS_PEER_REDUCE_CTAS: persistent grid of the slab-wise peer reduce (0: one thread per voxel)
+  bool fc_v4 = false;                  // EMVS_FC_V4: four pixels per thread in the fuse + collapse sweep
+  int fc_zsplit = 4;                   // EMVS_FC_ZSPLIT: plane chunks of the fuse + collapse sweep
+  bool dbg_skip_merge = false, dbg_skip_zero = false;   // EMVS_DEBUG_SKIP_MERGE / _ZERO: timing experiments, WRONG results
   uint64_t prefetch_generation = 0;    // bumped by every prefetch; emvs_context_prefetch_pending reports the pending one
   void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
   void* d_fc_part = nullptr; size_t fc_part_cap = 0;  // per-chunk (max, index) of the Z-split sweep
@@ -301,7 +307,7 @@ int peer_reduce_slab(emvs_context* ctx, emvs_exchange* ex, int cam, uint32_t sla
   if (band) {
     float* out = ex->band_buf + ((size_t)cam * ex->dimZ + k0) * band;
     // EMVS_PEER_REDUCE_CTAS: size of the persistent reduce grid (0: one thread per voxel, thousands of CTAs)
-    static const int reduce_ctas = env_int("EMVS_PEER_REDUCE_CTAS", 64);
+    const int reduce_ctas = ctx->peer_reduce_ctas;
     const uint32_t n_pix = ex->dimX * ex->dimY;
     if (reduce_ctas > 0 && p_lo % 4 == 0 && band % 4 == 0 && n_pix % 4 == 0 && (((size_t)k0 * band) % 4) == 0) {
       k_peer_reduce_band_v4<<<(unsigned)reduce_ctas, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch,
@@ -507,7 +513,7 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     }
     static const bool merge_grouped = [] { const char* e = getenv("EMVS_MERGE_GROUPED"); return e ? atoi(e) != 0 : true; }();
     // timing experiments only (profiles/r2_interference.md): the DSI is WRONG with either of them set
-    static const bool dbg_skip_merge = env_int("EMVS_DEBUG_SKIP_MERGE", 0) != 0, dbg_skip_zero = env_int("EMVS_DEBUG_SKIP_ZERO", 0) != 0;
+    const bool dbg_skip_merge = ctx->dbg_skip_merge, dbg_skip_zero = ctx->dbg_skip_zero;
     if (dbg_skip_merge) {
     } else if (G > 1 && merge_grouped) {
       const dim3 mg(ceil_div(QW, 256 / G), QH, ceil_div(nk, G));
@@ -530,7 +536,7 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     {
       // re-zero the merged buffer.  Beside the persistent vote grid only 256-thread CTAs find a slot, and a capped
       // grid spreads the 79 MB of stores over the vote launch instead of bursting (EMVS_ZERO_CTAS=0: cudaMemsetAsync)
-      static const int zero_ctas = env_int("EMVS_ZERO_CTAS", 296);
+      const int zero_ctas = ctx->zero_ctas;
       const size_t n_f4 = (size_t)round_up_g(nk) * QW * QH * 4;
       if (dbg_skip_zero) {
       } else if (zero_ctas > 0) {
@@ -596,8 +602,7 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
   // (A float4-per-thread variant with the Z range split over warps was measured slower than this
   // one-pixel-per-thread sweep — 0.234 vs 0.209 ms for two 640x480x256 volumes, profiles/r1_fuse_collapse.md.)
   // The planes are split over 4 CTAs per pixel tile + a combine pass: 0.196 vs 0.209 ms (EMVS_FC_ZSPLIT overrides).
-  static const int zsplit_env = [] { const char* e = getenv("EMVS_FC_ZSPLIT"); return e ? atoi(e) : 4; }();
-  const uint32_t n_chunks = (uint32_t)std::max(1, std::min<int>(zsplit_env, (int)(dimZ / 16)));   // at least 16 planes per chunk
+  const uint32_t n_chunks = (uint32_t)std::max(1, std::min<int>(ctx->fc_zsplit, (int)(dimZ / 16)));   // at least 16 planes per chunk
   float* part_best = nullptr;
   uint32_t* part_k = nullptr;
   uint32_t per_chunk = dimZ;
@@ -610,8 +615,7 @@ int launch_fuse_collapse_n(emvs_context* ctx, const FuseArgs& A, uint32_t n_pix,
   }
   const uint32_t used_chunks = n_chunks > 1 ? (dimZ + per_chunk - 1) / per_chunk : 1;
   // EMVS_FC_V4=1: four pixels per thread (16-byte loads); needs 16-byte aligned planes
-  static const bool fc_v4 = env_int("EMVS_FC_V4", 0) != 0;
-  const bool v4 = fc_v4 && n_chunks > 1 && n_pix % 4 == 0;
+  const bool v4 = ctx->fc_v4 && n_chunks > 1 && n_pix % 4 == 0;
   const unsigned blocks4 = (n_pix / 4 + 127) / 128;
 #define LAUNCH_M(M, N)                                                                                                     \
   do {                                                                                                                     \
@@ -734,6 +738,12 @@ int emvs_context_create(int device, emvs_context** out)
   if (const char* env = getenv("EMVS_OVERLAP")) ctx->overlap = atoi(env) != 0;
   if (const char* env = getenv("EMVS_VOTE_KERNEL")) ctx->vote_tma = strcmp(env, "classic") != 0;
   if (const char* env = getenv("EMVS_VOTE_CTAS_PER_SM")) ctx->vote_ctas_per_sm = (uint32_t)std::min(8, std::max(1, atoi(env)));
+  ctx->zero_ctas = std::max(0, env_int("EMVS_ZERO_CTAS", ctx->zero_ctas));
+  ctx->peer_reduce_ctas = std::max(0, env_int("EMVS_PEER_REDUCE_CTAS", ctx->peer_reduce_ctas));
+  ctx->fc_v4 = env_int("EMVS_FC_V4", 0) != 0;
+  ctx->fc_zsplit = std::max(1, env_int("EMVS_FC_ZSPLIT", ctx->fc_zsplit));
+  ctx->dbg_skip_merge = env_int("EMVS_DEBUG_SKIP_MERGE", 0) != 0;
+  ctx->dbg_skip_zero = env_int("EMVS_DEBUG_SKIP_ZERO", 0) != 0;
   if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming);
