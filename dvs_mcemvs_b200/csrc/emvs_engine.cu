@@ -114,7 +114,7 @@ struct emvs_context {
   uint32_t vote_ctas_per_sm = 7;
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
   // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
-  int zero_ctas = 296;                 // EMVS_ZERO_CTAS: grid of the scratch re-zero kernel (0: cudaMemsetAsync)
+  int zero_ctas = 0;                   // EMVS_ZERO_CTAS: grid of a hand-rolled re-zero kernel; 0 (default, measured faster): cudaMemsetAsync
   int peer_reduce_ctas = 64;           // EMVS_PEER_REDUCE_CTAS: persistent grid of the slab-wise peer reduce (0: one thread per voxel)
   bool fc_v4 = false;                  // EMVS_FC_V4: four pixels per thread in the fuse + collapse sweep
   int fc_zsplit = 4;                   // EMVS_FC_ZSPLIT: plane chunks of the fuse + collapse sweep
@@ -534,8 +534,8 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     }
     ctx->launches++;
     {
-      // re-zero the merged buffer.  Beside the persistent vote grid only 256-thread CTAs find a slot, and a capped
-      // grid spreads the 79 MB of stores over the vote launch instead of bursting (EMVS_ZERO_CTAS=0: cudaMemsetAsync)
+      // re-zero the merged buffer (cudaMemsetAsync; EMVS_ZERO_CTAS=n selects a capped grid-stride kernel that spreads
+      // the 79 MB of stores over the vote launch — measured 1.3 % SLOWER, profiles/r2_interference.md)
       const int zero_ctas = ctx->zero_ctas;
       const size_t n_f4 = (size_t)round_up_g(nk) * QW * QH * 4;
       if (dbg_skip_zero) {

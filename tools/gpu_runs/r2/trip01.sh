@@ -5,6 +5,8 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out/r2
 O=gpurun_out/r2
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/t01_smi.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/t01_smoke.log 2>&1 || { echo "SMOKE FAILED"; tail -30 $O/t01_smoke.log; exit 1; }
+tail -2 $O/t01_smoke.log
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > $O/t01_pytest.log
 ( timeout 120 tools/vote_variants_bench csv ) > $O/t01_variants.csv 2> $O/t01_variants.err
 ( timeout 600 python tools/ab_bench.py ) > $O/t01_ab.jsonl 2> $O/t01_ab.err
