@@ -112,6 +112,7 @@ struct emvs_context {
   // build is issued; the persistent grid leaves one 256-thread slot per SM to the merge / exchange kernels
   unsigned int* d_work = nullptr;
   uint32_t vote_ctas_per_sm = 7;
+  int vote_split = -1;                 // EMVS_VOTE_SPLIT: log2 of work items per packet (0..2); -1: automatic
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
   // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
   int zero_ctas = 0;                   // EMVS_ZERO_CTAS: grid of a hand-rolled re-zero kernel; 0 (default, measured faster): cudaMemsetAsync
@@ -470,11 +471,19 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     if (use_tma) {
       // persistent grid: vote_ctas_per_sm CTAs per SM take packets from the slab's work counter; their event tiles
       // arrive by cp.async.bulk (TMA) into two shared-memory stages
-      const unsigned grid = (unsigned)std::min<size_t>(n_packets, (size_t)ctx->sm_count * ctx->vote_ctas_per_sm);
+      const size_t resident = (size_t)ctx->sm_count * ctx->vote_ctas_per_sm;
+      // work items per packet: whole packets when every resident CTA gets several of them, halves / quarters when a
+      // build is short (head of a split upload, a small shard) so that the dynamic queue can still balance the SMs
+      uint32_t sub = 0;
+      if (ctx->vote_split >= 0) sub = (uint32_t)ctx->vote_split;
+      else while (sub < 2 && (n_packets << sub) < 4 * resident) ++sub;
+      while (sub > 0 && (EMVS_PACKET_SIZE >> sub) / (kVoteThreads / G) < 8) --sub;   // keep the unrolled event loop whole
+      const size_t n_items = n_packets << sub;
+      const unsigned grid = (unsigned)std::min<size_t>(n_items, resident);
       const size_t smem_t = vote_tma_smem_bytes(nk);
       unsigned int* wc = ctx->d_work + k0 / slab;
 #define LAUNCH_VOTE_T(GG)                                                                                                 \
-  k_vote_tma<GG><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_packets, P, ctx->quad[b], \
+  k_vote_tma<GG><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_items, sub, P, ctx->quad[b], \
                                                      m->d_counts, wc)
       switch (G) {
         case 2: LAUNCH_VOTE_T(2); break;
@@ -738,6 +747,7 @@ int emvs_context_create(int device, emvs_context** out)
   if (const char* env = getenv("EMVS_OVERLAP")) ctx->overlap = atoi(env) != 0;
   if (const char* env = getenv("EMVS_VOTE_KERNEL")) ctx->vote_tma = strcmp(env, "classic") != 0;
   if (const char* env = getenv("EMVS_VOTE_CTAS_PER_SM")) ctx->vote_ctas_per_sm = (uint32_t)std::min(8, std::max(1, atoi(env)));
+  ctx->vote_split = std::min(2, std::max(-1, env_int("EMVS_VOTE_SPLIT", ctx->vote_split)));
   ctx->zero_ctas = std::max(0, env_int("EMVS_ZERO_CTAS", ctx->zero_ctas));
   ctx->peer_reduce_ctas = std::max(0, env_int("EMVS_PEER_REDUCE_CTAS", ctx->peer_reduce_ctas));
   ctx->fc_v4 = env_int("EMVS_FC_V4", 0) != 0;

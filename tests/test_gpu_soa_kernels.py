@@ -62,7 +62,8 @@ def test_soa_equals_aos_and_oracle(ctx, small_case):
 
 
 @pytest.mark.parametrize("env", [{"EMVS_VOTE_KERNEL": "classic"}, {"EMVS_VOTE_CTAS_PER_SM": "1"}, {"EMVS_VOTE_CTAS_PER_SM": "8"},
-                                 {"EMVS_ZERO_CTAS": "0"}, {"EMVS_VOTE_GROUP": "4"}, {"EMVS_VOTE_GROUP": "16"}],
+                                 {"EMVS_ZERO_CTAS": "296"}, {"EMVS_VOTE_GROUP": "4"}, {"EMVS_VOTE_GROUP": "16"},
+                                 {"EMVS_VOTE_SPLIT": "0"}, {"EMVS_VOTE_SPLIT": "2"}, {"EMVS_FC_V4": "1", "EMVS_FC_ZSPLIT": "8"}],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_vote_kernel_variants_agree(small_case, env):
     """The TMA-staged persistent kernel (default), the classic one-CTA-per-packet kernel and other grid / group /
@@ -88,6 +89,9 @@ def test_vote_kernel_variants_agree(small_case, env):
         "    m.build(case.events[i], case.packets[i])\n"           # and the scratch is clean again afterwards
         "    assert np.array_equal(m.counts(), inb_o)\n"
         "    np.testing.assert_allclose(m.dsi_.download(), dsi_o, rtol=1e-5, atol=1e-5)\n"
+        "    conf, idx, depth = m.dsi_.collapseMaxZSlice(m.raw_depths_vec_)\n"
+        "    vol = m.dsi_.download()\n"
+        "    assert np.array_equal(conf, vol.max(0)) and np.array_equal(idx, vol.argmax(0)) and np.array_equal(depth, m.raw_depths_vec_[idx])\n"
         "    m.close()\n"
         "print('variant ok')\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
