@@ -111,14 +111,14 @@ struct emvs_context {
   // k_vote_tma: one work counter per vote launch of a build (packets are handed out dynamically), zeroed when the
   // build is issued; the persistent grid leaves one 256-thread slot per SM to the merge / exchange kernels
   unsigned int* d_work = nullptr;
-  uint32_t vote_ctas_per_sm = 7;
+  uint32_t vote_ctas_per_sm = 6;
   int vote_split = -1;                 // EMVS_VOTE_SPLIT: log2 of work items per packet (0..2); -1: automatic
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
   // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
   int zero_ctas = 0;                   // EMVS_ZERO_CTAS: grid of a hand-rolled re-zero kernel; 0 (default, measured faster): cudaMemsetAsync
-  int peer_reduce_ctas = 64;           // EMVS_PEER_REDUCE_CTAS: persistent grid of the slab-wise peer reduce (0: one thread per voxel)
-  bool fc_v4 = false;                  // EMVS_FC_V4: four pixels per thread in the fuse + collapse sweep
-  int fc_zsplit = 4;                   // EMVS_FC_ZSPLIT: plane chunks of the fuse + collapse sweep
+  int peer_reduce_ctas = 1024;           // EMVS_PEER_REDUCE_CTAS: persistent grid of the slab-wise peer reduce (0: one thread per voxel)
+  bool fc_v4 = true;                   // EMVS_FC_V4: four pixels per thread in the fuse + collapse sweep (0: one pixel per thread)
+  int fc_zsplit = 8;                   // EMVS_FC_ZSPLIT: plane chunks of the fuse + collapse sweep
   bool dbg_skip_merge = false, dbg_skip_zero = false;   // EMVS_DEBUG_SKIP_MERGE / _ZERO: timing experiments, WRONG results
   uint64_t prefetch_generation = 0;    // bumped by every prefetch; emvs_context_prefetch_pending reports the pending one
   void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
@@ -128,7 +128,7 @@ struct emvs_context {
   emvs_packet* h_packets = nullptr; size_t h_packets_cap = 0;
   // evaluate_dsi on an idle pipeline: the head of the event list (split_percent %) is uploaded and voted first
   // while the tail is still crossing PCIe (see emvs_mapper_evaluate_dsi_flags); 0 disables
-  uint32_t split_percent = 25;
+  uint32_t split_percent = 15;
   size_t split_min_events = (size_t)1 << 20;
   // NCCL
   void* comm = nullptr;
@@ -476,7 +476,7 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
       // build is short (head of a split upload, a small shard) so that the dynamic queue can still balance the SMs
       uint32_t sub = 0;
       if (ctx->vote_split >= 0) sub = (uint32_t)ctx->vote_split;
-      else while (sub < 2 && (n_packets << sub) < 4 * resident) ++sub;
+      else while (sub < 2 && (n_packets << sub) < 8 * resident) ++sub;
       while (sub > 0 && (EMVS_PACKET_SIZE >> sub) / (kVoteThreads / G) < 8) --sub;   // keep the unrolled event loop whole
       const size_t n_items = n_packets << sub;
       const unsigned grid = (unsigned)std::min<size_t>(n_items, resident);
@@ -750,7 +750,7 @@ int emvs_context_create(int device, emvs_context** out)
   ctx->vote_split = std::min(2, std::max(-1, env_int("EMVS_VOTE_SPLIT", ctx->vote_split)));
   ctx->zero_ctas = std::max(0, env_int("EMVS_ZERO_CTAS", ctx->zero_ctas));
   ctx->peer_reduce_ctas = std::max(0, env_int("EMVS_PEER_REDUCE_CTAS", ctx->peer_reduce_ctas));
-  ctx->fc_v4 = env_int("EMVS_FC_V4", 0) != 0;
+  ctx->fc_v4 = env_int("EMVS_FC_V4", ctx->fc_v4 ? 1 : 0) != 0;
   ctx->fc_zsplit = std::max(1, env_int("EMVS_FC_ZSPLIT", ctx->fc_zsplit));
   ctx->dbg_skip_merge = env_int("EMVS_DEBUG_SKIP_MERGE", 0) != 0;
   ctx->dbg_skip_zero = env_int("EMVS_DEBUG_SKIP_ZERO", 0) != 0;

@@ -167,7 +167,7 @@ EMVS_API int emvs_context_sync(emvs_context* ctx);
 EMVS_API int emvs_context_set_slab(emvs_context* ctx, uint32_t planes_per_slab);
 /* Tuning of emvs_mapper_evaluate_dsi on an idle pipeline: the first `percent` % of the event list is uploaded and
  * voted first while the rest is still crossing PCIe, then the rest is voted into the same DSI (votes add).  Lists
- * shorter than `min_events` are built in one piece; percent = 0 disables.  Defaults: 25 %, 2^20 events
+ * shorter than `min_events` are built in one piece; percent = 0 disables.  Defaults: 15 %, 2^20 events
  * ($EMVS_UPLOAD_SPLIT overrides the percentage at context creation). */
 EMVS_API int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t min_events);
 /* Streaming callers (consecutive windows, main.cpp:177-431 full_seq loop): announce the event list of the NEXT

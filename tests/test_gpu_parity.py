@@ -110,7 +110,7 @@ def test_evaluate_dsi_split_upload(ctx, small_case, built_small, percent):
         assert np.array_equal(m.counts(), oracle[0][1])
         np.testing.assert_allclose(m.dsi_.download(), oracle[0][0], rtol=DSI_RTOL, atol=DSI_ATOL)
     finally:
-        ctx.set_upload_split(25)
+        ctx.set_upload_split(15)
         m.close()
 
 

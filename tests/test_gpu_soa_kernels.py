@@ -34,7 +34,7 @@ def test_soa_equals_aos_and_oracle(ctx, small_case):
         ctx.sync()
         ctx.set_upload_split(30, 4096)
         assert m.evaluateDSI(soa, tr, small_case.T_rv_w) is True
-        ctx.set_upload_split(25)
+        ctx.set_upload_split(15)
         assert np.array_equal(m.counts(), inb_o)
         np.testing.assert_allclose(m.dsi_.download(), dsi_o, rtol=DSI_RTOL, atol=DSI_ATOL)
         # prefetch: after it landed neither x, y nor t on the host matter any more
