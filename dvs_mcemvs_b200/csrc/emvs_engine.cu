@@ -111,7 +111,7 @@ struct emvs_context {
   // k_vote_tma: one work counter per vote launch of a build (packets are handed out dynamically), zeroed when the
   // build is issued; the persistent grid leaves one 256-thread slot per SM to the merge / exchange kernels
   unsigned int* d_work = nullptr;
-  uint32_t vote_ctas_per_sm = 6;
+  uint32_t vote_ctas_per_sm = 7;       // EMVS_VOTE_CTAS_PER_SM: resident CTAs per SM of the persistent vote grid (1..8)
   int vote_split = -1;                 // EMVS_VOTE_SPLIT: log2 of work items per packet (0..2); -1: automatic
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
   // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
@@ -471,6 +471,9 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     if (use_tma) {
       // persistent grid: vote_ctas_per_sm CTAs per SM take packets from the slab's work counter; their event tiles
       // arrive by cp.async.bulk (TMA) into two shared-memory stages
+      // 7 of the 8 CTA slots per SM: the eighth (and, at 32 registers per thread, an eighth of the register file) stays
+      // free for the merge / re-zero / peer-reduce kernels that run beside the votes.  Measured (profiles/r2_ab_knobs.md):
+      // 6 per SM is 2 % faster with device-resident inputs but 5 % slower through the host-buffer calls, 8 is the reverse
       const size_t resident = (size_t)ctx->sm_count * ctx->vote_ctas_per_sm;
       // work items per packet: whole packets when every resident CTA gets several of them, halves / quarters when a
       // build is short (head of a split upload, a small shard) so that the dynamic queue can still balance the SMs

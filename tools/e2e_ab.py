@@ -61,34 +61,39 @@ def main():
         mappers = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
         depths = mappers[0].raw_depths_vec_
 
+        calls = {}
+
+        def timed(label, f):
+            t0 = time.perf_counter()
+            r = f()
+            calls[label] = calls.get(label, 0.0) + time.perf_counter() - t0
+            return r
+
         def step(prefetch):
-            for m, ev, tr in zip(mappers, pinned, trajs):
-                assert m.evaluateDSI(ev, tr, T)
+            for i, (m, ev, tr) in enumerate(zip(mappers, pinned, trajs)):
+                assert timed(f"evaluateDSI{i}", lambda: m.evaluateDSI(ev, tr, T))
             if prefetch:
-                mappers[0].prefetch(pinned[0], trajs[0], T)
-            return api.fuse_collapse([m.dsi_ for m in mappers], method, depths)
+                timed("prefetch", lambda: mappers[0].prefetch(pinned[0], trajs[0], T))
+            return timed("fuse_collapse", lambda: api.fuse_collapse([m.dsi_ for m in mappers], method, depths))
 
         out = {"variant": name, "env": env}
         for label, pf in (("stock_ms", False), ("streaming_ms", True)):
             for _ in range(2):
                 step(pf)
             ctx.sync()
+            calls.clear()
+            ctx.profile_vote(True)
             t0 = time.perf_counter()
             for _ in range(a.steps):
                 step(pf)
             ctx.sync()
             out[label] = round((time.perf_counter() - t0) / a.steps * 1e3, 3)
+            vote_ms, n_vote = ctx.vote_time()
+            ctx.profile_vote(False)
+            out[label.replace("_ms", "_vote_ms_per_launch")] = round(vote_ms / max(n_vote, 1), 5)
+            out[label.replace("_ms", "_vote_ms_per_step")] = round(vote_ms / a.steps, 3)
+            out[label.replace("_ms", "_calls_ms")] = {k: round(v / a.steps * 1e3, 3) for k, v in calls.items()}
             ctx.prefetch_cancel()
-        # where the stock step spends its host time: each call blocks until its inputs are consumed / outputs are back
-        ctx.sync()
-        t0 = time.perf_counter()
-        mappers[0].evaluateDSI(pinned[0], trajs[0], T)
-        t1 = time.perf_counter()
-        mappers[1].evaluateDSI(pinned[1], trajs[1], T)
-        t2 = time.perf_counter()
-        api.fuse_collapse([m.dsi_ for m in mappers], method, depths)
-        t3 = time.perf_counter()
-        out["stock_calls_ms"] = [round((b - a_) * 1e3, 3) for a_, b in ((t0, t1), (t1, t2), (t2, t3))]
         print(json.dumps(out), flush=True)
         for m in mappers:
             m.close()
