@@ -1,9 +1,10 @@
 """Minimal ROS bag (format 2.0, uncompressed chunks) reader / writer for the two message types the
 mapping path consumes — no ROS installation needed.
 
-  geometry_msgs/PoseStamped  -> STAMPED_POSE_DTYPE control poses (what parse_rosbag_gt collects,
+  geometry_msgs/PoseStamped, geometry_msgs/PoseWithCovarianceStamped, nav_msgs/Odometry, vicon/Subject
+                             -> STAMPED_POSE_DTYPE control poses (what parse_rosbag_gt collects,
                                 mapper_emvs_stereo/src/data_loading.cpp:305-465; the bundled
-                                data/DSEC/*/pose.bag files are exactly this)
+                                data/DSEC/*/pose.bag files are PoseStamped)
   dvs_msgs/EventArray        -> EVENT_DTYPE events (data_loading.cpp:33-219); a serialised
                                 dvs_msgs/Event is 13 bytes {uint16 x, uint16 y, time ts, bool polarity},
                                 the in-memory struct the engine takes is the 16-byte padded one
@@ -175,7 +176,64 @@ def parse_camera_info(p):
     return dict(width=int(width), height=int(height), distortion_model=model, D=D, K=K, R=R, P=P)
 
 
-_POSE_TYPES = {"geometry_msgs/PoseStamped", "geometry_msgs/PoseWithCovarianceStamped"}
+# Pose-carrying message types of data_loading.cpp.  parse_rosbag (events + poses, :33-219) accepts the first three,
+# parse_rosbag_gt (:305-465) all four.  Wire layouts (ROS1 serialisation, little endian):
+#   geometry_msgs/PoseStamped                 Header, Point position (3 f64), Quaternion orientation (x y z w f64)
+#   geometry_msgs/PoseWithCovarianceStamped   the same followed by float64[36] covariance
+#   nav_msgs/Odometry                         Header, string child_frame_id, PoseWithCovariance pose, TwistWithCovariance twist
+#   vicon/Subject (EVIMO2)                    Header, string name, position (3 f64), orientation (x y z w f64), then
+#                                             occlusion flag / markers.  The vicon package is not vendored in the reference
+#                                             tree; this is the field order of the EVIMO recording tools' Subject.msg, and only
+#                                             the fields data_loading.cpp:115-141 reads (header.stamp, position, orientation)
+#                                             are decoded.
+_POSE_TYPES = {"geometry_msgs/PoseStamped", "geometry_msgs/PoseWithCovarianceStamped", "vicon/Subject"}
+_POSE_TYPES_GT = _POSE_TYPES | {"nav_msgs/Odometry"}
+
+
+def _skip_string(p, o):
+    (n,) = struct.unpack_from("<I", p, o)
+    return o + 4 + n
+
+
+def parse_pose_message(mtype, p):
+    """-> (stamp (sec, nsec), quaternion (w, x, y, z), position (x, y, z)) of one pose-carrying message."""
+    stamp, o = _skip_std_header(p)
+    if mtype in ("nav_msgs/Odometry", "vicon/Subject"):
+        o = _skip_string(p, o)            # child_frame_id / subject name
+    elif mtype not in _POSE_TYPES_GT:
+        raise ValueError(f"not a pose message type: {mtype}")
+    px, py, pz, qx, qy, qz, qw = struct.unpack_from("<7d", p, o)
+    return stamp, (qw, qx, qy, qz), (px, py, pz)
+
+
+def parse_rosbag_gt(path, pose_topic, tmin=0.0, tmax=float("inf"), origin=None):
+    """data_loading::parse_rosbag_gt (data_loading.cpp:305-465): the control poses of `pose_topic` — vicon/Subject,
+    geometry_msgs/PoseStamped, geometry_msgs/PoseWithCovarianceStamped or nav_msgs/Odometry messages — restricted to
+    [tmin, tmax] seconds after the process-wide first stamp and re-timed relative to it.  Same literal rules as
+    parse_rosbag: a pose past tmax is still inserted and stops the loop afterwards; an equal re-timed stamp does not
+    replace an earlier pose (std::map::insert).  Returns STAMPED_POSE_DTYPE sorted by stamp."""
+    origin = DEFAULT_ORIGIN if origin is None else origin
+    msgs = sorted(read_messages(path, topics={pose_topic}), key=lambda m: m[2])
+    poses, go_on = {}, True
+    for topic, mtype, _, p in msgs:
+        if not go_on:
+            break
+        if mtype not in _POSE_TYPES_GT:
+            continue
+        stamp, q, t = parse_pose_message(mtype, p)
+        if origin.stamp is None:
+            origin.stamp = stamp
+        rel = (stamp[0] - origin.stamp[0]) + 1e-9 * (stamp[1] - origin.stamp[1])
+        if rel < tmin:
+            continue
+        if rel > tmax:
+            go_on = False
+        poses.setdefault(_time_from_sec((stamp[0] + 1e-9 * stamp[1]) - origin.to_sec()), (q, t))
+    arr = np.zeros(len(poses), STAMPED_POSE_DTYPE)
+    for i, k in enumerate(sorted(poses)):
+        arr["sec"][i], arr["nsec"][i] = k
+        arr["T"]["q"][i], arr["T"]["t"][i] = poses[k]
+    return arr
 
 
 def parse_rosbag(path, event_topic, camera_info_topic=None, pose_topic=None, tmin=0.0, tmax=float("inf"),
@@ -225,8 +283,8 @@ def parse_rosbag(path, event_topic, camera_info_topic=None, pose_topic=None, tmi
                 ev_parts.append(e)
         elif topic == camera_info_topic and mtype == "sensor_msgs/CameraInfo":
             cam_info = parse_camera_info(p)
-        elif topic == pose_topic and mtype in _POSE_TYPES:
-            stamp, o = _skip_std_header(p)
+        elif topic == pose_topic and mtype in _POSE_TYPES:     # vicon/Subject, PoseStamped, PoseWithCovarianceStamped (:111-219)
+            stamp, q, t = parse_pose_message(mtype, p)
             if origin.stamp is None:
                 origin.stamp = stamp
             rel = (stamp[0] - origin.stamp[0]) + 1e-9 * (stamp[1] - origin.stamp[1])
@@ -234,11 +292,8 @@ def parse_rosbag(path, event_topic, camera_info_topic=None, pose_topic=None, tmi
                 continue
             if rel > tmax:
                 go_on = False
-            px, py, pz, qx, qy, qz, qw = struct.unpack_from("<7d", p, o)
             key = _time_from_sec((stamp[0] + 1e-9 * stamp[1]) - origin.to_sec())
-            poses.setdefault(key, ((qw, qx, qy, qz), (px, py, pz)))
-        elif topic == pose_topic and mtype == "vicon/Subject":
-            raise NotImplementedError("vicon/Subject poses (EVIMO2) are not supported by rosbag_lite")
+            poses.setdefault(key, (q, t))
     ev = np.concatenate(ev_parts) if ev_parts else np.zeros(0, EVENT_DTYPE)
     key = ev["sec"].astype(np.uint64) * np.uint64(1_000_000_000) + ev["nsec"].astype(np.uint64)
     ev = ev[np.argsort(key, kind="stable")]
@@ -272,22 +327,40 @@ def serialize_camera_info(info, sec=0, nsec=0):
             struct.pack("<II", 0, 0) + struct.pack("<IIIIB", 0, 0, 0, 0, 0))
 
 
+_POSE_MD5 = {"geometry_msgs/PoseStamped": "d3812c3cbc69362b77dc0b19b345f8f5",
+             "geometry_msgs/PoseWithCovarianceStamped": "953b798c0f514ff060a53a3498ce6246",
+             "nav_msgs/Odometry": "cd5e73d190d741a2f92e81eda573aca7",
+             "vicon/Subject": "*"}
+
+
 def write_bag(path, poses=None, pose_topic="/pose", events=None, event_topic="/dvs/events", sensor=(640, 480),
-              events_per_message=5000, camera_info=None, camera_info_topic="/dvs/camera_info", pose_with_covariance=False):
+              events_per_message=5000, camera_info=None, camera_info_topic="/dvs/camera_info", pose_with_covariance=False,
+              pose_type=None):
     """Writes one bag holding the given control poses (STAMPED_POSE_DTYPE), events (EVENT_DTYPE) and / or one
-    sensor_msgs/CameraInfo (a dict as parse_camera_info returns)."""
+    sensor_msgs/CameraInfo (a dict as parse_camera_info returns).  pose_type: one of the four pose-carrying message
+    types (default geometry_msgs/PoseStamped; pose_with_covariance=True selects PoseWithCovarianceStamped)."""
     conns, msgs = [], []   # msgs: (conn id, (sec, nsec), payload)
     if poses is not None:
         cid = len(conns)
-        if pose_with_covariance:
-            conns.append((pose_topic, "geometry_msgs/PoseWithCovarianceStamped", "953b798c0f514ff060a53a3498ce6246"))
-        else:
-            conns.append((pose_topic, "geometry_msgs/PoseStamped", "d3812c3cbc69362b77dc0b19b345f8f5"))
+        if pose_type is None:
+            pose_type = "geometry_msgs/PoseWithCovarianceStamped" if pose_with_covariance else "geometry_msgs/PoseStamped"
+        conns.append((pose_topic, pose_type, _POSE_MD5[pose_type]))
         for i, p in enumerate(np.asarray(poses, STAMPED_POSE_DTYPE)):
             q, t = p["T"]["q"], p["T"]["t"]
-            msgs.append((cid, (int(p["sec"]), int(p["nsec"])), _std_header(i, int(p["sec"]), int(p["nsec"])) +
-                         struct.pack("<7d", t[0], t[1], t[2], q[1], q[2], q[3], q[0]) +
-                         (struct.pack("<36d", *([0.0] * 36)) if pose_with_covariance else b"")))
+            pose = struct.pack("<7d", t[0], t[1], t[2], q[1], q[2], q[3], q[0])
+            hdr = _std_header(i, int(p["sec"]), int(p["nsec"]))
+            if pose_type == "geometry_msgs/PoseStamped":
+                payload = hdr + pose
+            elif pose_type == "geometry_msgs/PoseWithCovarianceStamped":
+                payload = hdr + pose + struct.pack("<36d", *([0.0] * 36))
+            elif pose_type == "nav_msgs/Odometry":      # child_frame_id, PoseWithCovariance, TwistWithCovariance
+                child = b"base_link"
+                payload = (hdr + struct.pack("<I", len(child)) + child + pose + struct.pack("<36d", *([0.0] * 36)) +
+                           struct.pack("<6d", *([0.0] * 6)) + struct.pack("<36d", *([0.0] * 36)))
+            else:                                       # vicon/Subject: name, position, orientation, occluded, no markers
+                name = b"subject"
+                payload = hdr + struct.pack("<I", len(name)) + name + pose + struct.pack("<BI", 0, 0)
+            msgs.append((cid, (int(p["sec"]), int(p["nsec"])), payload))
     if camera_info is not None:
         cid = len(conns)
         conns.append((camera_info_topic, "sensor_msgs/CameraInfo", "c9a58c1b0b154e0e6da7578cb991d214"))

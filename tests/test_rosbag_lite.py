@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+from dvs_mcemvs_b200 import _capi as capi
 from dvs_mcemvs_b200 import rosbag_lite, synth
 
 
@@ -115,3 +116,30 @@ def test_parse_rosbag_windows_and_retimes_like_data_loading(tmp_path):
     assert rosbag_lite._time_from_sec(1.9999999996) == (2, 0) and rosbag_lite._time_from_sec(0.25) == (0, 250000000)
     with pytest.raises(ValueError):
         rosbag_lite._time_from_sec(-1e-3)
+
+
+@pytest.mark.parametrize("pose_type", ["geometry_msgs/PoseStamped", "geometry_msgs/PoseWithCovarianceStamped",
+                                       "nav_msgs/Odometry", "vicon/Subject"])
+def test_parse_rosbag_gt_reads_every_pose_message_type(tmp_path, pose_type):
+    """data_loading::parse_rosbag_gt (data_loading.cpp:305-465) accepts four pose-carrying message types; every one
+    round-trips through the writer, is re-timed to the first stamp and windowed with the stop-AFTER-the-message rule."""
+    t0 = 1234.5
+    tp = t0 + np.linspace(0.0, 2.0, 41)
+    poses = np.zeros(41, capi.STAMPED_POSE_DTYPE)
+    poses["sec"], poses["nsec"] = synth._split_time(tp)
+    ang = np.linspace(0, 0.3, 41)
+    poses["T"]["q"][:, 0], poses["T"]["q"][:, 2] = np.cos(ang / 2), np.sin(ang / 2)
+    poses["T"]["t"] = np.stack([np.linspace(0, 1, 41), np.linspace(2, 3, 41), np.linspace(-1, 0, 41)], 1)
+    bag = str(tmp_path / "poses.bag")
+    rosbag_lite.write_bag(bag, poses=poses, pose_type=pose_type)
+    got = rosbag_lite.parse_rosbag_gt(bag, "/pose", origin=rosbag_lite.TimeOrigin())
+    assert len(got) == 41 and got["sec"][0] == 0 and got["nsec"][0] == 0            # re-timed to the first stamp
+    np.testing.assert_allclose(got["sec"] + 1e-9 * got["nsec"], tp - t0, atol=2e-9)
+    assert got["T"].tobytes() == poses["T"].tobytes()                                # position + quaternion bit for bit
+    win = rosbag_lite.parse_rosbag_gt(bag, "/pose", tmin=0.5, tmax=1.0, origin=rosbag_lite.TimeOrigin())
+    rel = win["sec"] + 1e-9 * win["nsec"]
+    assert rel[0] == pytest.approx(0.5, abs=1e-6) and rel[-1] == pytest.approx(1.05, abs=1e-6)   # the first pose past tmax is kept
+    assert len(rosbag_lite.parse_rosbag_gt(bag, "/other", origin=rosbag_lite.TimeOrigin())) == 0
+    # the events + poses loader takes the same messages, except nav_msgs/Odometry (data_loading.cpp:111-219 has no such branch)
+    _, p, _ = rosbag_lite.parse_rosbag(bag, "/dvs/events", None, "/pose", origin=rosbag_lite.TimeOrigin())
+    assert len(p) == (0 if pose_type == "nav_msgs/Odometry" else 41)
