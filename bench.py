@@ -26,8 +26,10 @@ milliseconds (fuse + argmax) and the build-only Mevents/s are reported beside it
   parity         the maps / counts / checksums of the timed configuration against the CPU oracle (N = 1) and
                  against an unsharded build on rank 0 (N > 1); outside every timed region.
 
-Multi-GPU: every rank owns one packet-aligned sub-interval of EVERY camera's event stream.
-  --scaling weak   (default) 5 M events/camera/GPU — the stream gets denser with N;
+Multi-GPU: the GPUs are divided over the cameras and each GPU builds one packet-aligned
+sub-interval of ITS camera's event stream (--sharding 2d, the default when the GPU count is a multiple of the camera
+count); --sharding interval makes every GPU build a sub-interval of EVERY camera (round 1).
+  --scaling weak   (default) n_cameras x 5 M events per GPU — the streams get denser with N;
   --scaling strong --events-per-cam E: E events/camera in total, split over the N GPUs (BASELINE.json configs[3] is
                    E = 20 M on 8 GPUs).
 Launched by torchrun; torch.distributed is only the rendezvous / barrier plumbing.
@@ -72,6 +74,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sharding", default="2d", choices=["2d", "interval"],
+                    help="multi-GPU work split: 2d = camera x event sub-interval (one camera per GPU when the GPU count is a "
+                         "multiple of the camera count; needs the peer exchange), interval = every GPU builds its sub-interval "
+                         "of every camera")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU DSI exchange: fused reduce+fuse+argmax over NVLink peer memory, or "
                          "slab-wise ncclAllReduce overlapped with voting followed by a local sweep")
@@ -274,7 +280,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from dvs_mcemvs_b200 import _capi as capi
-    from dvs_mcemvs_b200 import api, shard
+    from dvs_mcemvs_b200 import api, shard, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -301,36 +307,61 @@ def run_b200(args):
 
     strong = args.scaling == "strong" and world > 1
     n_ev = args.events_per_cam
-    # weak: rank r owns sample r of the stream; strong: every rank sees the same list and builds its packet range
-    sc, cams, events_all, trajs, T_rv_w, method, desc = make_workload(n_ev, 0 if strong else rank, args.kind)
+    sc, _, method, desc = synth.config(WORKLOAD, events_per_cam=n_ev)
+    cams = sc.rig.cams
     n_cams = len(cams)
+    trajs = [sc.trajectory(i) for i in range(n_cams)]
+    T_rv_w = sc.T_rv_w()
+    # Sharding.  2d: camera x sub-interval — the GPUs are divided over the cameras, a rank builds ONE
+    # camera's sub-interval (needs the peer exchange and a GPU count that is a multiple of the camera count).
+    # interval: every rank builds a sub-interval of EVERY camera (round 1; the only form the NCCL exchange supports).
+    group = shard.camera_groups(n_cams, world) if (world > 1 and args.sharding == "2d" and args.exchange == "peer") else 0
+    if group:
+        my_cam, part = divmod(rank, group)
+        local = [my_cam]
+    else:
+        part, local = rank, list(range(n_cams))
+    need_all = strong and rank == 0 and not args.no_parity          # rank 0 builds every camera unsharded for the parity block
     mappers = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
     ltrajs = [api.LinearTrajectory(t) for t in trajs]
     depths = mappers[0].raw_depths_vec_
     dimX, dimY, dimZ = mappers[0].dsi_.size_
 
-    packets_all = [m.packetize(ev, tr, T_rv_w) for m, ev, tr in zip(mappers, events_all, ltrajs)]
+    # ---- this rank's event lists ---------------------------------------------------------------
+    events, packets = {}, {}            # camera -> this rank's list / packets (first_event relative to the list)
+    events_all, packets_all = {}, {}    # strong scaling: the whole list of a camera and its packets
     if strong:
-        # this rank's packet range of every camera; only the events those packets reference are kept (rebased)
-        events, packets = [], []
-        for cam, lo, hi in shard.plan([len(p) for p in packets_all], world, rank):
-            pk = packets_all[cam][lo:hi].copy()
+        # a camera's list is the same on every rank; a rank builds packet range `part` of its group
+        for c in (range(n_cams) if need_all else local):
+            events_all[c] = sc.events(c, n_ev, args.kind, stream=0)
+            packets_all[c] = mappers[c].packetize(events_all[c], ltrajs[c], T_rv_w)
+        for c in local:
+            n_parts = group if group else world
+            lo, hi = shard.split_range(len(packets_all[c]), n_parts)[part]
+            pk = packets_all[c][lo:hi].copy()
             if len(pk):
                 e_lo = int(pk["first_event"][0])
                 # one event past the last packet: the packet loop's strict '<' (mapper_emvs_stereo.cpp:88) needs it to
                 # form that packet when this slice is packetised on its own (the e2e leg)
-                e_hi = min(len(events_all[cam]), int(pk["first_event"][-1]) + capi.PACKET_SIZE + 1)
+                e_hi = min(len(events_all[c]), int(pk["first_event"][-1]) + capi.PACKET_SIZE + 1)
                 pk["first_event"] -= e_lo
-                events.append(np.ascontiguousarray(events_all[cam][e_lo:e_hi]))
+                events[c] = np.ascontiguousarray(events_all[c][e_lo:e_hi])
             else:
-                events.append(events_all[cam][:0].copy())
-            packets.append(pk)
+                events[c] = events_all[c][:0].copy()
+            packets[c] = pk
     else:
-        events, packets = events_all, packets_all
+        # weak scaling: n_cams * n_ev events per GPU.  2d: all of them belong to the rank's camera (sample `part` of that
+        # camera's stream); interval: n_ev of every camera (sample `rank`)
+        for c in local:
+            n_local = n_ev * n_cams if group else n_ev
+            events[c] = sc.events(c, n_local, args.kind, stream=part)
+            packets[c] = mappers[c].packetize(events[c], ltrajs[c], T_rv_w)
+        if world == 1:
+            events_all, packets_all = events, packets
 
     # ---- device-resident inputs for `value` -------------------------------------------------
-    d_events = [torch.from_numpy(ev.view(np.uint8).reshape(-1).copy()).cuda() for ev in events]
-    d_packets = [torch.from_numpy(pk.view(np.uint8).reshape(-1).copy()).cuda() for pk in packets]
+    d_events = {c: torch.from_numpy(events[c].view(np.uint8).reshape(-1).copy()).cuda() for c in local}
+    d_packets = {c: torch.from_numpy(packets[c].view(np.uint8).reshape(-1).copy()).cuda() for c in local}
     torch.cuda.synchronize()
     d_conf = torch.empty(dimY * dimX, dtype=torch.float32, device="cuda")
     d_depth = torch.empty(dimY * dimX, dtype=torch.float32, device="cuda")
@@ -348,12 +379,13 @@ def run_b200(args):
             out = [None] * world
             dist.all_gather_object(out, b)
             return out
-        peer = api.PeerExchange(ctx, grids, world, rank, allgather)
+        peer = api.PeerExchange(ctx, grids, world, rank, allgather,
+                                participants=shard.participants(n_cams, world, two_d=bool(group)))
 
     def builds_device():
-        for m, de, dp, pk, ev in zip(mappers, d_events, d_packets, packets, events):
-            m.build_device(de.data_ptr(), len(ev), dp.data_ptr(), len(pk), allreduce=world > 1 and peer is None,
-                           peer_reduce=peer is not None)
+        for c in local:
+            mappers[c].build_device(d_events[c].data_ptr(), len(events[c]), d_packets[c].data_ptr(), len(packets[c]),
+                                    allreduce=world > 1 and peer is None, peer_reduce=peer is not None)
 
     def step_device():
         if peer is not None:
@@ -407,9 +439,14 @@ def run_b200(args):
     t_depth.stop()
     ctx.sync()
     build_ms, depth_ms = t_build.elapsed_ms(), t_depth.elapsed_ms()
-    counts_local = [m.counts() for m in mappers]       # accepted (event, plane) votes of this rank's shard (peer mode)
-    votes = int(sum(int(c.sum()) for c in counts_local))
-    n_voted_events = sum(len(pk) for pk in packets) * capi.PACKET_SIZE
+    # accepted (event, plane) votes of this rank's builds, per camera (zero rows for the cameras it does not build)
+    counts_local = np.zeros((n_cams, dimZ), np.uint64)
+    for c in local:
+        counts_local[c] = mappers[c].counts()
+    votes = int(sum(int(counts_local[c].sum()) for c in local))
+    if world > 1 and peer is None:
+        votes //= world                                # the NCCL path has already summed the counters over the ranks
+    n_voted_events = sum(len(packets[c]) for c in local) * capi.PACKET_SIZE
     if peer is not None:
         maps_dev = peer.download()                     # the exchanged maps of the timed configuration (every rank has them)
     else:
@@ -419,26 +456,27 @@ def run_b200(args):
     # ---- e2e: host buffers through the reference-facing calls ---------------------------------
     e2e_runs = {}
     if not args.no_e2e:
-        h_events = []
-        for ev in events:
-            buf = api.pinned_empty(ev.shape, ev.dtype)
-            buf[...] = ev
-            h_events.append(buf)
-        h_soa = [api.EventsSoA.from_events(ev, pinned=True) for ev in events]
+        h_events = {}
+        for c in local:
+            buf = api.pinned_empty(events[c].shape, events[c].dtype)
+            buf[...] = events[c]
+            h_events[c] = buf
+        h_soa = {c: api.EventsSoA.from_events(events[c], pinned=True) for c in local}
         if strong:   # the slice of a rank, packetised on its own, must give that rank's packets of the global list
-            for m, ev, tr, pk in zip(mappers, h_events, ltrajs, packets):
-                mine = m.packetize(ev, tr, T_rv_w)
-                assert mine is not None and mine.tobytes() == pk.tobytes(), "sub-interval packets differ from the global packet list"
+            for c in local:
+                mine = mappers[c].packetize(h_events[c], ltrajs[c], T_rv_w)
+                assert mine is not None and mine.tobytes() == packets[c].tobytes(), "sub-interval packets differ from the global packet list"
 
         def step_host(lists, prefetch):
             if peer is not None:
                 peer.begin()
-            for m, ev, tr in zip(mappers, lists, ltrajs):
-                assert m.evaluateDSI(ev, tr, T_rv_w, allreduce=world > 1 and peer is None, peer_reduce=peer is not None)
+            for c in local:
+                assert mappers[c].evaluateDSI(lists[c], ltrajs[c], T_rv_w, allreduce=world > 1 and peer is None,
+                                              peer_reduce=peer is not None)
             if prefetch:
                 # streaming caller: the NEXT step's first event list starts crossing PCIe now, under this step's
                 # votes (every step still uploads every list once, inside the timed region)
-                mappers[0].prefetch(lists[0], ltrajs[0], T_rv_w)
+                mappers[local[0]].prefetch(lists[local[0]], ltrajs[local[0]], T_rv_w)
             if peer is not None:
                 peer.fuse_collapse(method, d_tab)
                 return peer.download()
@@ -449,7 +487,7 @@ def run_b200(args):
                 step_host(lists, prefetch)
             ctx.prefetch_cancel()
             if prefetch:
-                mappers[0].prefetch(lists[0], ltrajs[0], T_rv_w)    # what the previous window's step would have announced
+                mappers[local[0]].prefetch(lists[local[0]], ltrajs[local[0]], T_rv_w)   # what the previous window's step would have announced
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
@@ -458,7 +496,7 @@ def run_b200(args):
             barrier()
             e2e_s = (time.perf_counter() - t0) / args.steps
             ctx.prefetch_cancel()
-            h2d = sum(len(ev) for ev in events) * bytes_per_event + sum(pk.nbytes for pk in packets) + depths.nbytes
+            h2d = sum(len(events[c]) for c in local) * bytes_per_event + sum(packets[c].nbytes for c in local) + depths.nbytes
             d2h = conf.nbytes + idx.nbytes + depth.nbytes
             return e2e_s, h2d, d2h, (conf, idx, depth)
 
@@ -470,7 +508,7 @@ def run_b200(args):
     parity = None
     if not args.no_parity:
         parity = parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv_w, packets_all, events_all, events,
-                              packets, method, depths, maps_dev, counts_local, mean_square, strong, peer,
+                              packets, local, group, method, depths, maps_dev, counts_local, mean_square, strong, peer,
                               {k: v[3] for k, v in e2e_runs.items()})
 
     # ---- reduce over ranks ------------------------------------------------------------------
@@ -490,7 +528,7 @@ def run_b200(args):
 
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
-    total_events = float(n_cams * n_ev) if strong else sum_over_ranks(float(n_cams * n_ev))
+    total_events = float(n_cams * n_ev) if strong else sum_over_ranks(float(sum(len(events[c]) for c in local)))
     value = total_events / (ms_step * 1e-3) / 1e6
     votes_all = sum_over_ranks(float(votes))
     vote_ms_max = max_over_ranks(vote_ms)
@@ -514,18 +552,21 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
+        n_builds = max(len(local), 1)
         roof = roofline_block(peak, peak_src, votes, n_voted_events, vote_ms / args.steps, vote_launches / args.steps, ms_step,
-                              n_cams, n_ev if not strong else sum(len(e) for e in events) // max(n_cams, 1), dimX, dimY, dimZ)
+                              n_builds, sum(len(events[c]) for c in local) // n_builds, dimX, dimY, dimZ)
+        sharding = ("none" if world == 1 else
+                    (f"camera x event sub-interval: {group} GPU(s) per camera, each builds one camera's sub-interval" if group else
+                     "event sub-interval: every GPU builds its sub-interval of every camera")
+                    + ("; slab-wise reduce of each GPU's row band over NVLink peer memory under the votes, then fuse+argmax of "
+                       "the band and peer stores of the maps" if peer is not None else
+                       "; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting"))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(args, n_cams, (dimX, dimY, dimZ), method, world),
-            "config_detail": {"description": desc,
-                              "sharding": ("none" if world == 1 else
-                                           "event sub-interval per GPU; slab-wise reduce of each GPU's row band over NVLink peer memory under the votes, then fuse+argmax of the band and peer stores of the maps"
-                                           if peer is not None else
-                                           "event sub-interval per GPU; ncclAllReduce(sum) per Z-slab of each camera DSI, overlapped with voting")},
+            "config_detail": {"description": desc, "sharding": sharding},
             "build_mevents_per_s": total_events / (build_ms * 1e-3) / 1e6, "build_ms": build_ms,
             "depth_map_ms": depth_ms, "accepted_votes_per_step": int(votes_all),
             "vote_ms_per_launch_max_over_ranks": vote_ms_max / max(vote_launches, 1),
@@ -541,7 +582,7 @@ def run_b200(args):
             cb = parity.get("_cpu_baseline") if parity else None
             if cb is None:
                 _CPU_WORKLOAD.setdefault((min(args.cpu_sample_events, n_ev), args.kind),
-                                         (sc, cams, events_all, trajs, T_rv_w, method, desc))
+                                         (sc, cams, [events[c] for c in range(n_cams)], trajs, T_rv_w, method, desc))
                 cb, _, _ = cpu_reference(args, n_ev)
             out["cpu_baseline"] = cb
         if parity:
@@ -557,20 +598,21 @@ def run_b200(args):
 
 
 def parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv_w, packets_all, events_all, events, packets,
-                 method, depths, maps_dev, counts_local, mean_square, strong, peer, e2e_maps):
+                 local, group, method, depths, maps_dev, counts_local, mean_square, strong, peer, e2e_maps):
     """N = 1: the timed configuration's counts / maps / checksums against the CPU oracle on the same events (the run
     that is also the cpu_baseline).  N > 1: the exchanged maps and the summed counts against an UNSHARDED build of all
     ranks' events on rank 0's GPU (itself oracle-checked at N = 1).  Returns a dict on rank 0, None elsewhere."""
     from oracle import parity as P
     conf, idx, depth = maps_dev
+    n_cams = len(cams)
     if world == 1:
         n_ev = args.events_per_cam
         if min(args.cpu_sample_events, n_ev) != n_ev:
             return {"skipped": "the CPU sample is smaller than the workload (--cpu-sample-events): no full-size oracle run"}
-        _CPU_WORKLOAD[(n_ev, args.kind)] = (sc, cams, events_all, trajs, T_rv_w, method, "")
+        _CPU_WORKLOAD[(n_ev, args.kind)] = (sc, cams, [events[c] for c in range(n_cams)], trajs, T_rv_w, method, "")
         cb, _, art = cpu_reference(args, n_ev, keep=True)
         p = P.compare_maps(conf, idx, depth, art["conf"], art["idx"], art["depth"], art["fused"])
-        p["counts_exact"] = bool(all(np.array_equal(c, o) for c, o in zip(counts_local, art["counts"])))
+        p["counts_exact"] = bool(all(np.array_equal(counts_local[c], art["counts"][c]) for c in range(n_cams)))
         p["mean_square_gpu"] = mean_square
         p["mean_square_oracle"] = art["mean_square"]
         p["mean_square_rel"] = float(max(abs(g - o) / max(abs(o), 1e-300) for g, o in zip(mean_square, art["mean_square"])))
@@ -582,8 +624,7 @@ def parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv
         p["_cpu_baseline"] = cb
         return p
     # ---- N > 1 ------------------------------------------------------------------------------
-    dimZ = len(depths)
-    cnt = torch.from_numpy(np.stack(counts_local).astype(np.int64)).cuda()
+    cnt = torch.from_numpy(counts_local.astype(np.int64)).cuda()
     if peer is not None:
         dist.all_reduce(cnt)          # peer mode keeps per-rank counts: the job's counts are their sum
     cnt = cnt.cpu().numpy().astype(np.uint64)
@@ -591,18 +632,22 @@ def parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv
     if strong:
         if rank == 0:
             full = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
-            for m, ev, pk in zip(full, events_all, packets_all):
-                m.build(ev, pk)
+            for c, m in enumerate(full):
+                m.build(events_all[c], packets_all[c])
     else:
-        # weak scaling: rank 0 accumulates every rank's stream into one DSI per camera (votes add)
-        for cam in range(len(cams)):
-            ev_t = torch.from_numpy(events[cam].view(np.uint8).reshape(-1).copy()).cuda()
-            pk_n = torch.tensor([len(packets[cam])], dtype=torch.int64, device="cuda")
-            sizes = [torch.zeros_like(pk_n) for _ in range(world)]
-            dist.all_gather(sizes, pk_n)
-            max_pk = int(max(int(s.item()) for s in sizes))
-            pk_pad = np.zeros(max_pk, packets[cam].dtype)
-            pk_pad[:len(packets[cam])] = packets[cam]
+        # weak scaling: rank 0 accumulates every rank's list(s) into one DSI per camera (votes add)
+        seen = set()
+        for slot in range(len(local)):            # the same number of lists on every rank
+            c = local[slot]
+            ev_t = torch.from_numpy(events[c].view(np.uint8).reshape(-1).copy()).cuda()
+            meta = torch.tensor([len(packets[c]), c, len(events[c])], dtype=torch.int64, device="cuda")
+            metas = [torch.zeros_like(meta) for _ in range(world)]
+            dist.all_gather(metas, meta)
+            metas = [[int(v) for v in t.tolist()] for t in metas]
+            max_pk = max(mm[0] for mm in metas)
+            assert all(mm[2] == len(events[c]) for mm in metas), "ranks hold lists of different lengths"
+            pk_pad = np.zeros(max_pk, packets[c].dtype)
+            pk_pad[:len(packets[c])] = packets[c]
             pk_t = torch.from_numpy(pk_pad.view(np.uint8).reshape(-1).copy()).cuda()
             ev_list = [torch.empty_like(ev_t) for _ in range(world)] if rank == 0 else None
             pk_list = [torch.empty_like(pk_t) for _ in range(world)] if rank == 0 else None
@@ -611,10 +656,11 @@ def parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv
             torch.cuda.synchronize()     # the engine reads these tensors on its own stream
             if rank == 0:
                 if full is None:
-                    full = [api.MapperEMVS(ctx, c, sc.shape) for c in cams]
+                    full = [api.MapperEMVS(ctx, cc, sc.shape) for cc in cams]
                 for r in range(world):
-                    full[cam].build_device(ev_list[r].data_ptr(), len(events[cam]), pk_list[r].data_ptr(), int(sizes[r].item()),
-                                           accumulate=r > 0)
+                    n_pk_r, cam_r, n_ev_r = metas[r]
+                    full[cam_r].build_device(ev_list[r].data_ptr(), n_ev_r, pk_list[r].data_ptr(), n_pk_r, accumulate=cam_r in seen)
+                    seen.add(cam_r)
                 ctx.sync()
             del ev_list, pk_list
     p = None
@@ -624,7 +670,7 @@ def parity_block(args, world, rank, ctx, api, dist, torch, sc, cams, trajs, T_rv
         api.fuse_collapse([m.dsi_ for m in full], method, depths, fused_out=fused_g)
         p = P.compare_maps(conf, idx, depth, conf_f, idx_f, depth_f, fused_g.download())
         fused_g.close()
-        p["counts_exact"] = bool(all(np.array_equal(cnt[i], full[i].counts()) for i in range(len(cams))))
+        p["counts_exact"] = bool(all(np.array_equal(cnt[i], full[i].counts()) for i in range(n_cams)))
         for name, (c2, i2, d2) in e2e_maps.items():
             q = P.compare_maps(c2, i2, d2, conf_f, idx_f, depth_f)
             q["idx_mismatches_are_near_ties"] = None

@@ -138,6 +138,7 @@ _PROTOTYPES = {
     "emvs_exchange_blob_bytes": (C.c_int, [_vp, C.POINTER(_sz)]),
     "emvs_exchange_export": (C.c_int, [_vp, _vp]),
     "emvs_exchange_import": (C.c_int, [_vp, _vp]),
+    "emvs_exchange_set_participants": (C.c_int, [_vp, _vp]),
     "emvs_exchange_begin": (C.c_int, [_vp]),
     "emvs_exchange_fuse_collapse": (C.c_int, [_vp, C.c_int, _vp]),
     "emvs_exchange_maps": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),

@@ -444,12 +444,15 @@ class PeerExchange:
     allgather: callable(bytes) -> list of every rank's bytes in rank order (e.g. built on
     torch.distributed.all_gather_object); used once to exchange the CUDA IPC handles."""
 
-    def __init__(self, ctx, grids, n_ranks, rank, allgather):
+    def __init__(self, ctx, grids, n_ranks, rank, allgather, participants=None):
+        """participants: optional [n_cams][n_ranks] table (shard.participants) for camera x sub-interval sharding:
+        rank r builds camera c iff participants[c][r]; default: every rank builds every camera."""
         self.ctx, self.grids = ctx, list(grids)
         arr = (C.c_void_p * len(grids))(*[g._h for g in grids])
         h = C.c_void_p()
         check(_lib().emvs_exchange_create(ctx._h, arr, len(grids), int(n_ranks), int(rank), C.byref(h)))
         self._h = h
+        self._n_ranks = int(n_ranks)
         self.size_ = grids[0].size_
         n = C.c_size_t(0)
         check(_lib().emvs_exchange_blob_bytes(self._h, C.byref(n)))
@@ -459,6 +462,13 @@ class PeerExchange:
         assert len(blobs) == n_ranks and all(len(b) == n.value for b in blobs)
         cat = np.frombuffer(b"".join(blobs), np.uint8).copy()
         check(_lib().emvs_exchange_import(self._h, ptr(cat)))
+        if participants is not None:
+            self.set_participants(participants)
+
+    def set_participants(self, participants):
+        tab = np.ascontiguousarray(participants, np.uint8)
+        assert tab.shape == (len(self.grids), self._n_ranks)
+        check(_lib().emvs_exchange_set_participants(self._h, ptr(tab)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -183,6 +183,7 @@ struct emvs_exchange {
   unsigned int epoch = 0;
   bool imported = false;
   bool band_round = false;         // emvs_exchange_begin was called: builds reduce their slabs into band_buf
+  int first_local_cam = 0;         // lowest camera this rank builds (emvs_exchange_set_participants)
 };
 
 namespace {
@@ -291,12 +292,36 @@ int ncclAllReduceU64_checked(const NcclApi* api, emvs_context* ctx, unsigned lon
 // Slab-wise reduce-scatter over NVLink peer memory (EMVS_BUILD_PEER_REDUCE).  `after` is the stream on which
 // planes [k0, k0+nk) of camera `cam` become final on this rank (the merge stream): the "slab built" epoch is
 // published to every rank from there, and the band reduce is ordered behind it on the communication stream.
+// launches the band reduce of (cam, slab) on the communication stream (it waits for the slab flags of the ranks that
+// build `cam`)
+void launch_band_reduce(emvs_context* ctx, emvs_exchange* ex, int cam, uint32_t slab_idx, uint32_t k0, uint32_t nk)
+{
+  const uint32_t word = kFlagWordsPhase + ((uint32_t)cam * kMaxSlabs + slab_idx) * kMaxPeerRanks;
+  const uint32_t p_lo = ex->row_lo * ex->dimX, p_hi = ex->row_hi * ex->dimX, band = p_hi - p_lo;
+  if (!band) return;
+  float* out = ex->band_buf + ((size_t)cam * ex->dimZ + k0) * band;
+  // EMVS_PEER_REDUCE_CTAS: size of the grid-stride reduce grid (0: one thread per voxel)
+  const int reduce_ctas = ctx->peer_reduce_ctas;
+  const uint32_t n_pix = ex->dimX * ex->dimY;
+  if (reduce_ctas > 0 && p_lo % 4 == 0 && band % 4 == 0 && n_pix % 4 == 0) {
+    k_peer_reduce_band_v4<<<(unsigned)reduce_ctas, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch,
+                                                                               40000000000LL, ex->flags + 16, p_lo, p_hi, n_pix,
+                                                                               k0, nk, out);
+  } else {
+    const dim3 grid((band + 255) / 256, nk);
+    k_peer_reduce_band<<<grid, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch, 40000000000LL,
+                                                           ex->flags + 16, p_lo, p_hi, n_pix, k0, nk, out);
+  }
+  ctx->launches++;
+}
+
 int peer_reduce_slab(emvs_context* ctx, emvs_exchange* ex, int cam, uint32_t slab_idx, uint32_t k0, uint32_t nk,
                      cudaStream_t after)
 {
   REQUIRE(slab_idx < kMaxSlabs, EMVS_ERR_INVALID, "peer_reduce: slab index out of range");
   const uint32_t word = kFlagWordsPhase + ((uint32_t)cam * kMaxSlabs + slab_idx) * kMaxPeerRanks;
   k_flag_signal_word<<<1, 32, 0, after>>>(ex->flag_ptrs, ex->n_ranks, word + (uint32_t)ex->rank, ex->epoch);
+  ctx->launches++;
   while (ctx->slab_events.size() <= slab_idx) {
     cudaEvent_t e;
     CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -304,23 +329,14 @@ int peer_reduce_slab(emvs_context* ctx, emvs_exchange* ex, int cam, uint32_t sla
   }
   CUDA_TRY(cudaEventRecord(ctx->slab_events[slab_idx], after));
   CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->slab_events[slab_idx], 0));
-  const uint32_t p_lo = ex->row_lo * ex->dimX, p_hi = ex->row_hi * ex->dimX, band = p_hi - p_lo;
-  if (band) {
-    float* out = ex->band_buf + ((size_t)cam * ex->dimZ + k0) * band;
-    // EMVS_PEER_REDUCE_CTAS: size of the persistent reduce grid (0: one thread per voxel, thousands of CTAs)
-    const int reduce_ctas = ctx->peer_reduce_ctas;
-    const uint32_t n_pix = ex->dimX * ex->dimY;
-    if (reduce_ctas > 0 && p_lo % 4 == 0 && band % 4 == 0 && n_pix % 4 == 0 && (((size_t)k0 * band) % 4) == 0) {
-      k_peer_reduce_band_v4<<<(unsigned)reduce_ctas, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch,
-                                                                                 40000000000LL, ex->flags + 16, p_lo, p_hi, n_pix,
-                                                                                 k0, nk, out);
-    } else {
-      const dim3 grid((band + 255) / 256, nk);
-      k_peer_reduce_band<<<grid, 256, 0, ctx->comm_stream>>>(ex->args, cam, ex->flags + word, ex->epoch, 40000000000LL,
-                                                             ex->flags + 16, p_lo, p_hi, n_pix, k0, nk, out);
-    }
-  }
-  ctx->launches += 2;
+  launch_band_reduce(ctx, ex, cam, slab_idx, k0, nk);
+  // Camera x sub-interval sharding: the cameras this rank does not build are reduced for ITS row band too.  Their
+  // slab reduces ride on the slab loop of the rank's first own camera (every rank walks the same slabs at about the
+  // same pace, so the flags they wait for are published around the same time; a rank only ever waits for slabs
+  // that its peers publish from their own vote / merge pipeline, so the slowest rank never blocks).
+  if (cam == ex->first_local_cam)
+    for (int c = 0; c < ex->n_cams; ++c)
+      if (!((ex->args.cam_ranks[c] >> ex->rank) & 1u)) launch_band_reduce(ctx, ex, c, slab_idx, k0, nk);
   return EMVS_OK;
 }
 
@@ -360,6 +376,8 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     for (int c = 0; c < ex->n_cams; ++c)
       if (ex->local_dsi[c] == g->d) peer_cam = c;
     REQUIRE(peer_cam >= 0, EMVS_ERR_INVALID, "build: this mapper's DSI is not part of the active exchange");
+    REQUIRE((ex->args.cam_ranks[peer_cam] >> ex->rank) & 1u, EMVS_ERR_INVALID,
+            "build: this rank is not a participant of that camera (emvs_exchange_set_participants)");
   }
   const NcclApi* nccl = nullptr;
   if (reduce) {
@@ -2087,6 +2105,7 @@ int emvs_exchange_create(emvs_context* ctx, emvs_grid* const* grids, int n_cams,
   REQUIRE(ex, EMVS_ERR_INVALID, "out of host memory");
   ex->ctx = ctx;
   ex->n_cams = n_cams; ex->n_ranks = n_ranks; ex->rank = rank;
+  for (int c = 0; c < kMaxPeerCams; ++c) ex->args.cam_ranks[c] = c < n_cams ? ((1u << n_ranks) - 1u) : 0u;   // every rank builds every camera
   ex->dimX = grids[0]->dimX; ex->dimY = grids[0]->dimY; ex->dimZ = grids[0]->dimZ;
   for (int c = 0; c < n_cams; ++c) ex->local_dsi[c] = grids[c]->d;
   const size_t n_pix = (size_t)ex->dimX * ex->dimY;
@@ -2133,6 +2152,24 @@ int emvs_exchange_destroy(emvs_exchange* ex)
   cudaFree(ex->band_buf);
   context_release(ex->ctx);
   delete ex;
+  return EMVS_OK;
+}
+
+int emvs_exchange_set_participants(emvs_exchange* ex, const uint8_t* builds /* n_cams * n_ranks */)
+{
+  REQUIRE(ex && builds, EMVS_ERR_INVALID, "exchange_set_participants: NULL argument");
+  REQUIRE(!ex->band_round, EMVS_ERR_STATE, "exchange_set_participants: a round is in progress");
+  uint32_t masks[kMaxPeerCams] = {};
+  int first_local = -1;
+  for (int c = 0; c < ex->n_cams; ++c) {
+    for (int r = 0; r < ex->n_ranks; ++r)
+      if (builds[(size_t)c * ex->n_ranks + r]) masks[c] |= 1u << r;
+    REQUIRE(masks[c] != 0u, EMVS_ERR_INVALID, "exchange_set_participants: a camera that no rank builds");
+    if (first_local < 0 && ((masks[c] >> ex->rank) & 1u)) first_local = c;
+  }
+  REQUIRE(first_local >= 0, EMVS_ERR_INVALID, "exchange_set_participants: this rank builds no camera");
+  for (int c = 0; c < ex->n_cams; ++c) ex->args.cam_ranks[c] = masks[c];
+  ex->first_local_cam = first_local;
   return EMVS_OK;
 }
 

@@ -33,6 +33,35 @@ def plan(n_packets_per_camera, world, rank):
     return [(cam, *split_range(n, world)[rank]) for cam, n in enumerate(n_packets_per_camera)]
 
 
+def camera_groups(n_cams, world):
+    """Camera x sub-interval sharding: when the GPUs divide evenly over the cameras, camera c is
+    built by the group of g = world / n_cams consecutive ranks [c*g, (c+1)*g).  -> g, or 0 when that is not possible
+    (fewer GPUs than cameras, or not a multiple): every rank then builds a sub-interval of every camera (plan())."""
+    if n_cams >= 1 and world >= n_cams and world % n_cams == 0:
+        return world // n_cams
+    return 0
+
+
+def plan2d(n_packets_per_camera, world, rank):
+    """-> [(camera, packet_lo, packet_hi)] for `rank` under camera x sub-interval sharding: ONE camera per rank, its
+    packet list split over the g ranks of the camera's group.  Compared with plan() a rank votes twice as many events
+    of half as many cameras: half the per-slab merge / re-zero / exchange work for the same votes, and nothing to sum
+    across groups.  Falls back to plan() when the GPUs do not divide evenly over the cameras."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    g = camera_groups(len(n_packets_per_camera), world)
+    if g == 0:
+        return plan(n_packets_per_camera, world, rank)
+    cam, part = divmod(rank, g)
+    return [(cam, *split_range(n_packets_per_camera[cam], g)[part])]
+
+
+def participants(n_cams, world, two_d=True):
+    """builds[c][r] = 1 iff rank r builds camera c (the table emvs_exchange_set_participants takes)."""
+    g = camera_groups(n_cams, world) if two_d else 0
+    return [[1 if (g == 0 or r // g == c) else 0 for r in range(world)] for c in range(n_cams)]
+
+
 def row_bands(dimY, world):
     """Row band of the depth/confidence maps owned by each rank in the fused reduce+fuse+argmax
     sweep: [(row_lo, row_hi)] * world."""

@@ -388,6 +388,12 @@ EMVS_API int emvs_exchange_destroy(emvs_exchange* ex);
 EMVS_API int emvs_exchange_blob_bytes(const emvs_exchange* ex, size_t* out);
 EMVS_API int emvs_exchange_export(emvs_exchange* ex, uint8_t* blob);
 EMVS_API int emvs_exchange_import(emvs_exchange* ex, const uint8_t* all_blobs /* n_ranks * blob_bytes */);
+/* Camera x sub-interval sharding ("give each camera G/C GPUs and split its packet list").  builds[c *
+ * n_ranks + r] != 0 iff rank r builds (a sub-interval of) camera c; the same table on every rank.  Camera c is then
+ * summed over ITS ranks only, nobody reads or waits for the others' grid of that camera, and a rank builds only its
+ * own cameras between emvs_exchange_begin and emvs_exchange_fuse_collapse.  Default: every rank builds every camera.
+ * Every camera needs at least one rank and every rank at least one camera. */
+EMVS_API int emvs_exchange_set_participants(emvs_exchange* ex, const uint8_t* builds);
 /* Optional overlapped form of a round: emvs_exchange_begin, then build every camera of the exchange with
  * EMVS_BUILD_PEER_REDUCE (same order on every rank), then emvs_exchange_fuse_collapse, which in that case only
  * runs a local sweep over the already-reduced band and distributes it.  Without begin, fuse_collapse does the

@@ -52,11 +52,16 @@ def main():
         # (a) fused path: partial DSIs stay partial, one sweep over peer memory produces the maps
         ex = api.PeerExchange(ctx, [m.dsi_ for m in mappers], world, rank, allgather)
         peer_results = []
-        for rep in range(4):   # repeated rounds: the epoch flags must keep working; even = one exposed sweep,
-            banded = rep % 2 == 1   # odd = slab-wise band reduce overlapped with voting
+        two_d_possible = shard.camera_groups(len(cams), world) > 0
+        for rep in range(8 if two_d_possible else 4):   # repeated rounds: the epoch flags must keep working; even = one exposed
+            banded = rep % 2 == 1                       # sweep, odd = slab-wise band reduce overlapped with voting
+            two_d = rep >= 4                            # rounds 4-7: camera x sub-interval sharding (one camera per rank)
+            if rep in (0, 4):
+                ex.set_participants(shard.participants(len(cams), world, two_d=two_d))
             if banded:
                 ex.begin()
-            for cam, lo, hi in shard.plan([len(p) for p in packets], world, rank):
+            plan = shard.plan2d if two_d else shard.plan
+            for cam, lo, hi in plan([len(p) for p in packets], world, rank):
                 mappers[cam].build(events[cam], packets[cam][lo:hi], peer_reduce=banded)
             ex.fuse_collapse(method, mappers[0].depths_device_ptr())
             peer_results.append(ex.download())

@@ -36,12 +36,14 @@ def test_two_rank_alg2_sharded_matches_process_2():
 
 def test_two_rank_bench_parity_weak_and_strong():
     """bench.py's own parity block at N = 2 (exchanged maps and summed counts vs an unsharded build on rank 0), for
-    the weak-scaling default and for the fixed-total (strong) split of BASELINE.json configs[3], at a reduced size."""
+    the weak-scaling default and for the fixed-total (strong) split of BASELINE.json configs[3] under camera x
+    sub-interval sharding (the default), and for sub-interval-only sharding, at a reduced size."""
     import json
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    for extra in (["--scaling", "weak", "--events-per-cam", "300000"], ["--scaling", "strong", "--events-per-cam", "600000"]):
+    for extra in (["--scaling", "weak", "--events-per-cam", "300000"], ["--scaling", "strong", "--events-per-cam", "600000"],
+                  ["--scaling", "weak", "--events-per-cam", "300000", "--sharding", "interval"]):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "2",
                "--warmup", "1", "--no-cpu-baseline"] + extra
