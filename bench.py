@@ -332,7 +332,10 @@ def run_b200(args):
     events_all, packets_all = {}, {}    # strong scaling: the whole list of a camera and its packets
     if strong:
         # a camera's list is the same on every rank; a rank builds packet range `part` of its group
-        for c in (range(n_cams) if need_all else local):
+        for c in range(n_cams):
+            if not (need_all or c in local):
+                sc.skip_events()        # keep the scene's seed sequence in step with the ranks that do generate this list
+                continue
             events_all[c] = sc.events(c, n_ev, args.kind, stream=0)
             packets_all[c] = mappers[c].packetize(events_all[c], ltrajs[c], T_rv_w)
         for c in local:
@@ -352,7 +355,10 @@ def run_b200(args):
     else:
         # weak scaling: n_cams * n_ev events per GPU.  2d: all of them belong to the rank's camera (sample `part` of that
         # camera's stream); interval: n_ev of every camera (sample `rank`)
-        for c in local:
+        for c in range(n_cams):
+            if c not in local:
+                sc.skip_events()
+                continue
             n_local = n_ev * n_cams if group else n_ev
             events[c] = sc.events(c, n_local, args.kind, stream=part)
             packets[c] = mappers[c].packetize(events[c], ltrajs[c], T_rv_w)

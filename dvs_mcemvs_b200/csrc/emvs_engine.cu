@@ -371,7 +371,8 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
   emvs_exchange* ex = peer ? ctx->active_exchange : nullptr;
   int peer_cam = -1;
   if (peer) {
-    REQUIRE(!accumulate && !reduce, EMVS_ERR_INVALID, "build: EMVS_BUILD_PEER_REDUCE excludes ACCUMULATE and ALLREDUCE");
+    // (with ACCUMULATE this must be the LAST build into the DSI of the round: its merged slabs are announced as final)
+    REQUIRE(!reduce, EMVS_ERR_INVALID, "build: EMVS_BUILD_PEER_REDUCE excludes EMVS_BUILD_ALLREDUCE");
     REQUIRE(ex && ex->band_round, EMVS_ERR_STATE, "build: EMVS_BUILD_PEER_REDUCE needs emvs_exchange_begin");
     for (int c = 0; c < ex->n_cams; ++c)
       if (ex->local_dsi[c] == g->d) peer_cam = c;
@@ -1778,8 +1779,11 @@ static int evaluate_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_st
   // PCIe under the head's vote kernels; the tail is then voted with EMVS_BUILD_ACCUMULATE into the same DSI
   // (voting is a sum over events, so head + tail == whole list up to float summation order; the per-plane
   // counters add exactly).  When the stream is busy (the previous camera is still voting) the whole upload is
-  // already hidden and the list is built in one piece.  The slab-wise exchanges need final slabs: no split.
-  const bool exchange = (flags & (EMVS_BUILD_ALLREDUCE | EMVS_BUILD_PEER_REDUCE)) != 0;
+  // already hidden and the list is built in one piece.  The slab-wise exchanges need final slabs: with the peer
+  // reduce the head is a plain build and only the tail build (the last one into the DSI) announces its slabs; the
+  // NCCL allreduce form is not split.
+  const bool exchange = (flags & EMVS_BUILD_ALLREDUCE) != 0;
+  const int head_flags = flags & ~EMVS_BUILD_PEER_REDUCE;
   size_t n_head = 0;
   if (ctx->split_percent && !exchange && n_events >= ctx->split_min_events && n_events >= 4 * (size_t)EMVS_PACKET_SIZE) {
     const cudaError_t q = cudaStreamQuery(ctx->stream);
@@ -1794,16 +1798,15 @@ static int evaluate_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_st
     const size_t n_pk_head = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
                                                   n_head, ctx->h_packets, max_pk);
     if (n_pk_head) {
-      rc = build_from_host(m, ev, ctx->h_packets, n_pk_head, flags, true, n_head, n_events);
+      rc = build_from_host(m, ev, ctx->h_packets, n_pk_head, head_flags, true, n_head, n_events);
       if (rc) return rc;
       const size_t n_pk_tail = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
                                                     n_events, ctx->h_packets + n_pk_head, max_pk - n_pk_head);
-      if (n_pk_tail) {
+      if (n_pk_tail || (flags & EMVS_BUILD_PEER_REDUCE)) {   // (an empty tail still has to announce the slabs to the peers)
         rc = build_from_host(m, ev, ctx->h_packets + n_pk_head, n_pk_tail, flags | EMVS_BUILD_ACCUMULATE, true);
         if (rc) return rc;
-      } else {
-        CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse its list on return
       }
+      if (!n_pk_tail) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse its list on return
       return EMVS_OK;
     }
     // no packet in the head (every pose lookup missed): upload the rest and build in one piece

@@ -210,6 +210,12 @@ class Scene:
         ok &= (xi >= 0) & (xi < cam.width) & (yi >= 0) & (yi < cam.height)
         return xi, yi, ok
 
+    def skip_events(self):
+        """Advance the scene's seed sequence exactly as one events() call does, without generating anything: processes
+        that generate different subsets of the cameras' lists stay in step (the k-th events() call of a Scene seeds its
+        generator from the k-th draw of the scene's own generator)."""
+        self.rng.integers(1 << 62)
+
     def events(self, cam_idx, n_events, kind="structured", chunk=2_000_000, stream=0):
         """`stream` selects an independent event sample of the same scene, window and trajectory
         (a shard of a denser stream: multi-GPU sub-interval sharding)."""

@@ -148,7 +148,9 @@ enum {
   EMVS_BUILD_PEER_REDUCE = 4  /* multi-GPU, fused exchange (emvs_exchange_begin ... emvs_exchange_fuse_collapse):
                                  every Z-slab, once merged, is announced to the peers and this rank's row band of
                                  it is summed over all ranks straight from their HBM (NVLink peer loads) into a
-                                 local band buffer, on a side stream under the votes of the next slab.           */
+                                 local band buffer, on a side stream under the votes of the next slab.  May be
+                                 combined with EMVS_BUILD_ACCUMULATE for the LAST of several builds into one DSI
+                                 (its merged slabs are the ones announced as final).                              */
 };
 
 typedef struct emvs_context emvs_context;  /* one CUDA device + stream + scratch              */

@@ -65,6 +65,24 @@ def main():
                 mappers[cam].build(events[cam], packets[cam][lo:hi], peer_reduce=banded)
             ex.fuse_collapse(method, mappers[0].depths_device_ptr())
             peer_results.append(ex.download())
+        # the host-buffer call with the split upload (head voted while the tail crosses PCIe, only the tail build
+        # announces its slabs to the peers): every rank hands evaluateDSI the slice of events its packets cover
+        ex.set_participants(shard.participants(len(cams), world, two_d=two_d_possible))
+        ctx.set_upload_split(30, 4096)
+        for rep in range(2):
+            ctx.sync()                                  # idle pipeline: the split path is taken
+            ex.begin()
+            plan = shard.plan2d if two_d_possible else shard.plan
+            for cam, lo, hi in plan([len(p) for p in packets], world, rank):
+                pk = packets[cam][lo:hi]
+                if len(pk) == 0:
+                    mappers[cam].build(events[cam], pk, peer_reduce=True)
+                    continue
+                e_lo, e_hi = int(pk["first_event"][0]), min(len(events[cam]), int(pk["first_event"][-1]) + 1025)
+                assert mappers[cam].evaluateDSI(events[cam][e_lo:e_hi], trajs[cam], T, peer_reduce=True)
+            ex.fuse_collapse(method, mappers[0].depths_device_ptr())
+            peer_results.append(ex.download())
+        ctx.set_upload_split(15)
         ex.close()
         for r in peer_results[1:]:   # every round re-votes with atomics, so rounds agree to float-sum tolerance only
             np.testing.assert_allclose(r[0], peer_results[0][0], rtol=1e-4, atol=1e-6)
