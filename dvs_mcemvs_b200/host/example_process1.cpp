@@ -117,6 +117,40 @@ int main()
       std::printf("wrote %s: %ld bytes\n", npy, sz);
       ok = ok && sz == 128 + (long)W * H * 64 * 4;
     } else ok = false;
+    // --- structure-of-arrays event list (x, y, t stored separately): the same DSI as the dvs_msgs::Event list ---
+    {
+      const std::vector<uint64_t> counts_aos = mapper0.voteCounts();
+      const double ms_aos = mapper0.dsi_.computeMeanSquare();
+      std::vector<uint16_t> sx(ev[0].size()), sy(ev[0].size());
+      std::vector<int64_t> st(ev[0].size());
+      for (size_t i = 0; i < ev[0].size(); ++i) {
+        sx[i] = ev[0][i].x; sy[i] = ev[0][i].y;
+        st[i] = (int64_t)ev[0][i].sec * 1000000000ll + ev[0][i].nsec;
+      }
+      const emvs_events_soa soa{sx.data(), sy.data(), st.data(), sx.size()};
+      ok = ok && mapper0.evaluateDSI(soa, traj0, T_rv_w);
+      ok = ok && mapper0.voteCounts() == counts_aos;                                    // integer observable: bit-exact
+      ok = ok && std::fabs(mapper0.dsi_.computeMeanSquare() - ms_aos) <= 1e-6 * ms_aos;  // float sums: atomic order only
+      std::printf("SoA evaluateDSI: counts %s, mean square %g vs %g\n", mapper0.voteCounts() == counts_aos ? "equal" : "DIFFER",
+                  mapper0.dsi_.computeMeanSquare(), ms_aos);
+    }
+    // --- assignment to a mapper's public dsi_ overwrites the volume the mapper keeps voting into (the reference's
+    //     plain member semantics, mapper_emvs_stereo.hpp:116), it does not detach the view ---
+    {
+      Grid3D copy0(mapper0.dsi_);                      // deep copy, like the reference's by-value arguments
+      mapper1.dsi_ = copy0;                            // same dimensions: copies INTO mapper1's volume
+      ok = ok && std::fabs(mapper1.dsi_.computeMeanSquare() - mapper0.dsi_.computeMeanSquare()) <= 1e-12 * mapper0.dsi_.computeMeanSquare();
+      ok = ok && mapper1.evaluateDSI(ev[1], traj1, T_rv_w);          // ... and the mapper still builds into THAT volume
+      emvs_host::Image<float> d1, c1;
+      emvs_host::Image<uint8_t> i1;
+      mapper1.getDepthMapFromDSI(d1, c1, i1);
+      double s = 0;
+      for (float v : c1.data) s += v;
+      ok = ok && s > 0 && std::fabs(mapper1.dsi_.computeMeanSquare() - mapper0.dsi_.computeMeanSquare()) > 1e-9;
+      bool threw = false;
+      try { Grid3D small(4, 3, 2); mapper1.dsi_ = small; } catch (const std::runtime_error&) { threw = true; }
+      ok = ok && threw;                                // different dimensions: an error, never a silently detached view
+    }
     std::printf(ok ? "example_process1 ok\n" : "example_process1 FAILED\n");
     return ok ? 0 : 1;
   } catch (const std::exception& e) {
