@@ -129,6 +129,7 @@ struct emvs_context {
   // evaluate_dsi on an idle pipeline: the head of the event list (split_percent %) is uploaded and voted first
   // while the tail is still crossing PCIe (see emvs_mapper_evaluate_dsi_flags); 0 disables
   uint32_t split_percent = 15;
+  int split_pieces = 3;                // EMVS_UPLOAD_PIECES: 2 = head + tail, 3 = p % / 3p % / rest
   size_t split_min_events = (size_t)1 << 20;
   // NCCL
   void* comm = nullptr;
@@ -777,6 +778,7 @@ int emvs_context_create(int device, emvs_context** out)
   ctx->dbg_skip_merge = env_int("EMVS_DEBUG_SKIP_MERGE", 0) != 0;
   ctx->dbg_skip_zero = env_int("EMVS_DEBUG_SKIP_ZERO", 0) != 0;
   if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
+  ctx->split_pieces = std::min(3, std::max(2, env_int("EMVS_UPLOAD_PIECES", ctx->split_pieces)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_pk_free[b], cudaEventDisableTiming);
@@ -1792,31 +1794,42 @@ static int evaluate_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_st
     else CUDA_TRY(q);
   }
   if (n_head >= EMVS_PACKET_SIZE) {
-    rc = upload_events(ctx, ev, 0, n_head);
+    // Pieces [0, c0), [c0, c1), ..., [c_last, n): the first is small so that the first vote starts early, every later
+    // one is about as long to vote as the NEXT one takes to cross PCIe (votes ~3.9 ms, upload ~1.5 ms per 5 M events):
+    // with split_pieces = 3 and p = split_percent the cuts are p % and 4p % (10 / 30 / 60 % at p = 10).
+    size_t cuts[3];
+    int n_cuts = 0;
+    cuts[n_cuts++] = n_head;
+    if (ctx->split_pieces >= 3 && 4 * ctx->split_percent <= 70) {
+      const size_t c1 = (n_events / 100 * (4 * ctx->split_percent)) / EMVS_PACKET_SIZE * EMVS_PACKET_SIZE;
+      if (c1 > n_head + EMVS_PACKET_SIZE && c1 + EMVS_PACKET_SIZE < n_events) cuts[n_cuts++] = c1;
+    }
+    cuts[n_cuts] = n_events;   // sentinel: the end of the list
+    rc = upload_events(ctx, ev, 0, cuts[0]);
     if (rc) return rc;
-    size_t cur = 0;
-    const size_t n_pk_head = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
-                                                  n_head, ctx->h_packets, max_pk);
-    if (n_pk_head) {
-      rc = build_from_host(m, ev, ctx->h_packets, n_pk_head, head_flags, true, n_head, n_events);
-      if (rc) return rc;
-      const size_t n_pk_tail = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur,
-                                                    n_events, ctx->h_packets + n_pk_head, max_pk - n_pk_head);
-      if (n_pk_tail || (flags & EMVS_BUILD_PEER_REDUCE)) {   // (an empty tail still has to announce the slabs to the peers)
-        rc = build_from_host(m, ev, ctx->h_packets + n_pk_head, n_pk_tail, flags | EMVS_BUILD_ACCUMULATE, true);
+    size_t cur = 0, n_pk_done = 0;
+    bool built = false;
+    for (int k = 0; k <= n_cuts; ++k) {
+      const bool last = k == n_cuts;
+      const size_t limit = cuts[k];
+      const size_t n_pk = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur, limit,
+                                               ctx->h_packets + n_pk_done, max_pk - n_pk_done);
+      const size_t next_lo = last ? 0 : cuts[k], next_hi = last ? 0 : cuts[k + 1];
+      // only the LAST build into the DSI announces its slabs to the peers; an empty last piece still has to
+      const bool must_build = n_pk > 0 || (last && (!built || (flags & EMVS_BUILD_PEER_REDUCE)));
+      if (must_build) {
+        int f = last ? flags : head_flags;
+        if (built) f |= EMVS_BUILD_ACCUMULATE;
+        rc = build_from_host(m, ev, ctx->h_packets + n_pk_done, n_pk, f, true, next_lo, next_hi);
+        if (rc) return rc;
+        built = true;
+      } else if (!last) {
+        rc = copy_event_range(ctx, ev, next_lo, next_hi);   // nothing to vote in this piece: just keep the upload going
         if (rc) return rc;
       }
-      if (!n_pk_tail) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse its list on return
-      return EMVS_OK;
+      n_pk_done += n_pk;
     }
-    // no packet in the head (every pose lookup missed): upload the rest and build in one piece
-    rc = copy_event_range(ctx, ev, n_head, n_events);
-    if (rc) return rc;
-    const size_t n_pk = host_packetize_range(times, n_events, traj, n_poses, *T_rv_w, m->cam, m->virt, m->depths[0], &cur, n_events,
-                                             ctx->h_packets, max_pk);
-    rc = build_from_host(m, ev, ctx->h_packets, n_pk, flags, true);
-    if (rc) return rc;
-    if (n_pk == 0) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the caller may reuse its list on return
     return EMVS_OK;
   }
   // start the event upload first: the host packet stage (one pose + one 3x3 inverse per 1024

@@ -100,7 +100,7 @@ def test_evaluate_dsi_split_upload(ctx, small_case, built_small, percent):
         n0 = ctx.launch_count()
         assert m.evaluateDSI(small_case.events[0], tr, small_case.T_rv_w) is True
         n_whole = ctx.launch_count() - n0
-        assert n_split == 2 * n_whole      # head build + tail build really ran as two passes
+        assert n_split == (3 if 4 * percent <= 70 else 2) * n_whole      # the pieces really ran as separate passes (p %, 4p %, rest)
         assert np.array_equal(m.counts(), oracle[0][1])
         np.testing.assert_allclose(m.dsi_.download(), oracle[0][0], rtol=DSI_RTOL, atol=DSI_ATOL)
         # a second evaluateDSI with the split on must RESET, not keep accumulating into the previous result

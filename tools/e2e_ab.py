@@ -15,6 +15,11 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_VARIANTS = [
     ("default", {}),
+    ("pieces2_split15", {"EMVS_UPLOAD_PIECES": "2", "EMVS_UPLOAD_SPLIT": "15"}),
+    ("pieces3_split8", {"EMVS_UPLOAD_PIECES": "3", "EMVS_UPLOAD_SPLIT": "8"}),
+    ("pieces3_split10", {"EMVS_UPLOAD_PIECES": "3", "EMVS_UPLOAD_SPLIT": "10"}),
+    ("pieces3_split12", {"EMVS_UPLOAD_PIECES": "3", "EMVS_UPLOAD_SPLIT": "12"}),
+    ("pieces3_split15", {"EMVS_UPLOAD_PIECES": "3", "EMVS_UPLOAD_SPLIT": "15"}),
     ("classic", {"EMVS_VOTE_KERNEL": "classic"}),
     ("vote_split0", {"EMVS_VOTE_SPLIT": "0"}),
     ("vote_split2", {"EMVS_VOTE_SPLIT": "2"}),
