@@ -129,7 +129,7 @@ struct emvs_context {
   // evaluate_dsi on an idle pipeline: the head of the event list (split_percent %) is uploaded and voted first
   // while the tail is still crossing PCIe (see emvs_mapper_evaluate_dsi_flags); 0 disables
   uint32_t split_percent = 15;
-  int split_pieces = 3;                // EMVS_UPLOAD_PIECES: 2 = head + tail, 3 = p % / 3p % / rest
+  int split_pieces = 2;                // EMVS_UPLOAD_PIECES: 2 = head + tail (default), 3 = p % / 3p % / rest (measured slower: every extra piece is 16 short vote launches)
   size_t split_min_events = (size_t)1 << 20;
   // NCCL
   void* comm = nullptr;
@@ -1794,9 +1794,10 @@ static int evaluate_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_st
     else CUDA_TRY(q);
   }
   if (n_head >= EMVS_PACKET_SIZE) {
-    // Pieces [0, c0), [c0, c1), ..., [c_last, n): the first is small so that the first vote starts early, every later
-    // one is about as long to vote as the NEXT one takes to cross PCIe (votes ~3.9 ms, upload ~1.5 ms per 5 M events):
-    // with split_pieces = 3 and p = split_percent the cuts are p % and 4p % (10 / 30 / 60 % at p = 10).
+    // Pieces [0, c0), [c0, c1), ..., [c_last, n).  Default: head + tail.  With split_pieces = 3 and p = split_percent
+    // the cuts are p % and 4p % (10 / 30 / 60 % at p = 10): every piece's upload would hide under the previous piece's
+    // votes — measured SLOWER (10.8 vs 10.1 ms per stock step, profiles/r2_e2e.md): an extra piece is 16 more short vote
+    // launches + accumulating merges, which cost more than the exposed quarter millisecond of upload they hide.
     size_t cuts[3];
     int n_cuts = 0;
     cuts[n_cuts++] = n_head;

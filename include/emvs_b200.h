@@ -168,9 +168,8 @@ EMVS_API int emvs_context_sync(emvs_context* ctx);
 /* Tuning: number of Z-planes voted per pass over the event list (0 = automatic). */
 EMVS_API int emvs_context_set_slab(emvs_context* ctx, uint32_t planes_per_slab);
 /* Tuning of emvs_mapper_evaluate_dsi on an idle pipeline: the first `percent` % of the event list is uploaded and
- * voted first while the rest is still crossing PCIe, then the rest is voted into the same DSI (votes add) — in two
- * more pieces cut at 4 x percent % when that is <= 70 %, so that every piece's upload hides under the previous piece's
- * votes ($EMVS_UPLOAD_PIECES=2: head + tail only).  Lists
+ * voted first while the rest is still crossing PCIe, then the rest is voted into the same DSI (votes add);
+ * $EMVS_UPLOAD_PIECES=3 cuts the rest once more at 4 x percent % (measured slower).  Lists
  * shorter than `min_events` are built in one piece; percent = 0 disables.  Defaults: 15 %, 2^20 events
  * ($EMVS_UPLOAD_SPLIT overrides the percentage at context creation). */
 EMVS_API int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t min_events);

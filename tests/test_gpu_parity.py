@@ -100,7 +100,7 @@ def test_evaluate_dsi_split_upload(ctx, small_case, built_small, percent):
         n0 = ctx.launch_count()
         assert m.evaluateDSI(small_case.events[0], tr, small_case.T_rv_w) is True
         n_whole = ctx.launch_count() - n0
-        assert n_split == (3 if 4 * percent <= 70 else 2) * n_whole      # the pieces really ran as separate passes (p %, 4p %, rest)
+        assert n_split == 2 * n_whole      # head build + tail build really ran as two passes
         assert np.array_equal(m.counts(), oracle[0][1])
         np.testing.assert_allclose(m.dsi_.download(), oracle[0][0], rtol=DSI_RTOL, atol=DSI_ATOL)
         # a second evaluateDSI with the split on must RESET, not keep accumulating into the previous result
@@ -674,3 +674,35 @@ def test_config5_sweep_corners(ctx, O, dims, n_ev):
     assert np.array_equal(conf, dsi.max(axis=0)) and np.array_equal(idx, dsi.argmax(axis=0).astype(idx.dtype))
     assert np.array_equal(depth, depths[idx])
     m.close()
+
+
+def test_evaluate_dsi_three_piece_split(small_case):
+    """EMVS_UPLOAD_PIECES=3 (p %, 4p %, rest; off by default): the three builds add up to the one-piece DSI — counts
+    bit-exact.  Read when a context is created, hence a fresh process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "from conftest import Case\n"
+        "from dvs_mcemvs_b200 import api\n"
+        "case = Case('esim_small')\n"
+        "ctx = api.Context(0)\n"
+        "ctx.set_upload_split(10, 4096)\n"
+        "m = api.MapperEMVS(ctx, case.cams[0], case.shape)\n"
+        "n0 = ctx.launch_count()\n"
+        "assert m.evaluateDSI(case.events[0], api.LinearTrajectory(case.trajs[0]), case.T_rv_w)\n"
+        "n3 = ctx.launch_count() - n0\n"
+        "dsi_o, inb_o = case.oracle_dsi(0)\n"
+        "assert np.array_equal(m.counts(), inb_o)\n"
+        "np.testing.assert_allclose(m.dsi_.download(), dsi_o, rtol=1e-5, atol=1e-5)\n"
+        "ctx.set_upload_split(0)\n"
+        "ctx.sync(); n0 = ctx.launch_count()\n"
+        "assert m.evaluateDSI(case.events[0], api.LinearTrajectory(case.trajs[0]), case.T_rv_w)\n"
+        "assert n3 == 3 * (ctx.launch_count() - n0)\n"
+        "print('three pieces ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, EMVS_UPLOAD_PIECES="3"))
+    assert r.returncode == 0 and "three pieces ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
