@@ -96,3 +96,40 @@ def test_vote_kernel_variants_agree(small_case, env):
         "print('variant ok')\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_new_entry_points_report_errors(ctx, small_case):
+    """Round-2 entry points keep the C-ABI's conventions: bad arguments are status codes with a message, never aborts."""
+    import ctypes as C
+    from dvs_mcemvs_b200 import _capi as capi
+    lib = capi.load()
+    m = api.MapperEMVS(ctx, small_case.cams[0], small_case.shape)
+    tr = api.LinearTrajectory(small_case.trajs[0])
+    T = np.ascontiguousarray(small_case.T_rv_w, dtype=capi.POSE_DTYPE)
+    soa = api.EventsSoA.from_events(small_case.events[0])
+    try:
+        bad = capi.EventsSoA(soa.x.ctypes.data, None, soa.t_ns.ctypes.data, len(soa))
+        assert lib.emvs_mapper_evaluate_dsi_soa(m._h, C.byref(bad), capi.ptr(tr.poses), len(tr.poses), capi.ptr(T), 0) == capi.EMVS_ERR_INVALID
+        assert b"NULL event arrays" in lib.emvs_last_error()
+        es = soa.c_struct()
+        assert lib.emvs_mapper_evaluate_dsi_soa(m._h, C.byref(es), capi.ptr(tr.poses), 1, capi.ptr(T), 0) == capi.EMVS_ERR_INVALID
+        assert lib.emvs_mapper_prefetch_dsi_soa(m._h, None, capi.ptr(tr.poses), len(tr.poses), capi.ptr(T)) == capi.EMVS_ERR_INVALID
+        gen = C.c_uint64(7)
+        assert lib.emvs_context_prefetch_pending(ctx._h, C.byref(gen)) == capi.EMVS_OK and gen.value == 0
+        assert lib.emvs_context_prefetch_pending(ctx._h, None) == capi.EMVS_ERR_INVALID
+        assert lib.emvs_context_prefetch_cancel(ctx._h) == capi.EMVS_OK          # nothing pending: a no-op
+        # a one-rank exchange: the participants table is validated
+        arr = (C.c_void_p * 1)(m.dsi_._h)
+        ex = C.c_void_p()
+        assert lib.emvs_exchange_create(ctx._h, arr, 1, 1, 0, C.byref(ex)) == capi.EMVS_OK
+        none = np.zeros(1, np.uint8)
+        assert lib.emvs_exchange_set_participants(ex, capi.ptr(none)) == capi.EMVS_ERR_INVALID   # a camera nobody builds
+        assert lib.emvs_exchange_set_participants(ex, None) == capi.EMVS_ERR_INVALID
+        one = np.ones(1, np.uint8)
+        assert lib.emvs_exchange_set_participants(ex, capi.ptr(one)) == capi.EMVS_OK
+        assert lib.emvs_exchange_destroy(ex) == capi.EMVS_OK
+        # PEER_REDUCE without an active exchange round is a state error, not a crash
+        with pytest.raises(api.EmvsError):
+            m.build(small_case.events[0], small_case.packets[0], peer_reduce=True)
+    finally:
+        m.close()
