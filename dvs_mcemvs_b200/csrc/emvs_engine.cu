@@ -115,11 +115,16 @@ struct emvs_context {
   int vote_split = -1;                 // EMVS_VOTE_SPLIT: log2 of work items per packet (0..2); -1: automatic
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
   // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
-  int zero_ctas = 0;                   // EMVS_ZERO_CTAS: grid of a hand-rolled re-zero kernel; 0 (default, measured faster): cudaMemsetAsync
+  int zero_ctas = 592;                 // EMVS_ZERO_CTAS: grid of the re-zero kernel (its stores carry the evict_last hint); 0: cudaMemsetAsync
   int peer_reduce_ctas = 1024;           // EMVS_PEER_REDUCE_CTAS: persistent grid of the slab-wise peer reduce (0: one thread per voxel)
   bool fc_v4 = true;                   // EMVS_FC_V4: four pixels per thread in the fuse + collapse sweep (0: one pixel per thread)
   int fc_zsplit = 8;                   // EMVS_FC_ZSPLIT: plane chunks of the fuse + collapse sweep
   bool dbg_skip_merge = false, dbg_skip_zero = false;   // EMVS_DEBUG_SKIP_MERGE / _ZERO: timing experiments, WRONG results
+  // L2 eviction hints (0 none, 1 evict_first, 2 evict_last): EMVS_HINT_XY0 (event-tile bulk copies), EMVS_HINT_RED (vote
+  // REDs, 0 / 2), EMVS_HINT_DSI (1: streaming stores of the merged planes), EMVS_HINT_ZERO (re-zero kernel stores, needs
+  // EMVS_ZERO_CTAS > 0)
+  // Defaults measured in profiles/r2_l2_hints.md: -2.5 % per device-resident step, -1.4 % end to end and at N = 2.
+  int hint_xy0 = 1, hint_red = 2, hint_dsi = 1, hint_zero = 2;
   uint64_t prefetch_generation = 0;    // bumped by every prefetch; emvs_context_prefetch_pending reports the pending one
   void* d_out = nullptr;     size_t out_cap = 0;      // conf | depth | idx of a collapse
   void* d_fc_part = nullptr; size_t fc_part_cap = 0;  // per-chunk (max, index) of the Z-split sweep
@@ -352,10 +357,16 @@ struct EventSrc {
 constexpr uint32_t kMaxWorkCounters = 4096;    // vote launches (slabs) per build
 
 // gentle re-zeroing of a merged scratch buffer: 256-thread CTAs that fit beside the persistent vote grid
-__global__ void __launch_bounds__(256) k_zero_f4(float4* __restrict__ p, size_t n)
+__global__ void __launch_bounds__(256) k_zero_f4(float4* __restrict__ p, size_t n, int hint)
 {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (hint) {
+    const uint64_t pol = l2_policy(hint);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(p + i), "f"(0.f), "l"(pol) : "memory");
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = z;
 }
 
@@ -506,8 +517,14 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
       const size_t smem_t = vote_tma_smem_bytes(nk);
       unsigned int* wc = ctx->d_work + k0 / slab;
 #define LAUNCH_VOTE_T(GG)                                                                                                 \
-  k_vote_tma<GG><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_items, sub, P, ctx->quad[b], \
-                                                     m->d_counts, wc)
+  do {                                                                                                                    \
+    if (ctx->hint_red == 2)                                                                                               \
+      k_vote_tma<GG, 2><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_items, sub, P, \
+                                                            ctx->quad[b], m->d_counts, wc, ctx->hint_xy0);                \
+    else                                                                                                                  \
+      k_vote_tma<GG, 0><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_items, sub, P, \
+                                                            ctx->quad[b], m->d_counts, wc, ctx->hint_xy0);                \
+  } while (0)
       switch (G) {
         case 2: LAUNCH_VOTE_T(2); break;
         case 4: LAUNCH_VOTE_T(4); break;
@@ -550,7 +567,8 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     } else if (G > 1 && merge_grouped) {
       const dim3 mg(ceil_div(QW, 256 / G), QH, ceil_div(nk, G));
       float* dst = g->d + (size_t)k0 * dimX * dimY;
-#define LAUNCH_MERGE_G(GG) k_merge_quads_grouped<GG><<<mg, 256, 0, ms>>>(ctx->quad[b], dst, dimX, dimY, QW, QH, nk, accumulate ? 1 : 0)
+#define LAUNCH_MERGE_G(GG) \
+  k_merge_quads_grouped<GG><<<mg, 256, 0, ms>>>(ctx->quad[b], dst, dimX, dimY, QW, QH, nk, accumulate ? 1 : 0, ctx->hint_dsi)
       switch (G) {
         case 2: LAUNCH_MERGE_G(2); break;
         case 4: LAUNCH_MERGE_G(4); break;
@@ -566,13 +584,13 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     }
     ctx->launches++;
     {
-      // re-zero the merged buffer (cudaMemsetAsync; EMVS_ZERO_CTAS=n selects a capped grid-stride kernel that spreads
-      // the 79 MB of stores over the vote launch — measured 1.3 % SLOWER, profiles/r2_interference.md)
+      // re-zero the merged buffer: a grid-stride kernel whose stores carry the L2 evict_last hint, like the vote REDs that
+      // will land on these lines next (without the hints cudaMemsetAsync is the faster way, profiles/r2_l2_hints.md)
       const int zero_ctas = ctx->zero_ctas;
       const size_t n_f4 = (size_t)round_up_g(nk) * QW * QH * 4;
       if (dbg_skip_zero) {
       } else if (zero_ctas > 0) {
-        k_zero_f4<<<(unsigned)zero_ctas, 256, 0, ms>>>(ctx->quad[b], n_f4);
+        k_zero_f4<<<(unsigned)zero_ctas, 256, 0, ms>>>(ctx->quad[b], n_f4, ctx->hint_zero);
         ctx->launches++;
       } else {
         CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, n_f4 * sizeof(float4), ms));
@@ -777,6 +795,10 @@ int emvs_context_create(int device, emvs_context** out)
   ctx->fc_zsplit = std::max(1, env_int("EMVS_FC_ZSPLIT", ctx->fc_zsplit));
   ctx->dbg_skip_merge = env_int("EMVS_DEBUG_SKIP_MERGE", 0) != 0;
   ctx->dbg_skip_zero = env_int("EMVS_DEBUG_SKIP_ZERO", 0) != 0;
+  ctx->hint_xy0 = std::min(2, std::max(0, env_int("EMVS_HINT_XY0", ctx->hint_xy0)));
+  ctx->hint_red = env_int("EMVS_HINT_RED", ctx->hint_red) == 2 ? 2 : 0;
+  ctx->hint_dsi = env_int("EMVS_HINT_DSI", ctx->hint_dsi) != 0 ? 1 : 0;
+  ctx->hint_zero = std::min(2, std::max(0, env_int("EMVS_HINT_ZERO", ctx->hint_zero)));
   if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
   ctx->split_pieces = std::min(3, std::max(2, env_int("EMVS_UPLOAD_PIECES", ctx->split_pieces)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);

@@ -62,7 +62,8 @@ def test_soa_equals_aos_and_oracle(ctx, small_case):
 
 
 @pytest.mark.parametrize("env", [{"EMVS_VOTE_KERNEL": "classic"}, {"EMVS_VOTE_CTAS_PER_SM": "1"}, {"EMVS_VOTE_CTAS_PER_SM": "8"},
-                                 {"EMVS_ZERO_CTAS": "296"}, {"EMVS_VOTE_GROUP": "4"}, {"EMVS_VOTE_GROUP": "16"},
+                                 {"EMVS_ZERO_CTAS": "0", "EMVS_HINT_RED": "0", "EMVS_HINT_XY0": "0", "EMVS_HINT_DSI": "0"},
+                                 {"EMVS_HINT_XY0": "2", "EMVS_HINT_ZERO": "1"}, {"EMVS_VOTE_GROUP": "4"}, {"EMVS_VOTE_GROUP": "16"},
                                  {"EMVS_VOTE_SPLIT": "0"}, {"EMVS_VOTE_SPLIT": "2"}, {"EMVS_FC_V4": "0", "EMVS_FC_ZSPLIT": "4"}],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_vote_kernel_variants_agree(small_case, env):
