@@ -423,12 +423,15 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    ctx.profile_vote(True)
     ms_total = timed_device(args.steps)
-    vote_ms, vote_launches = ctx.vote_time()
-    ctx.profile_vote(False)
     n_launch = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    # per-launch timing of the vote kernel (roofline): a second pass of the same steps with an event pair around every
+    # vote launch — kept out of the `value` pass, where those extra stream operations would be inside the timed region
+    ctx.profile_vote(True)
+    timed_device(args.steps)
+    vote_ms, vote_launches = ctx.vote_time()
+    ctx.profile_vote(False)
 
     # stage split (a separate pass, not part of `value`): build vs depth-map (vs multi-GPU exchange)
     barrier()
