@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, trip 14 (1 GPU): the adopted configuration — full GPU suite, bench (configs[1]) with parity, reference arm,
-# strong-scaling N = 1 baseline (20 M events per camera), configs[2] (bar4) with parity, packet stage at 100 M events,
+# strong-scaling N = 1 baseline (20 M events per camera), configs[2] (bar4) with parity, ncu launch list + full captures (L2 hints adopted).
 
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out/r2
