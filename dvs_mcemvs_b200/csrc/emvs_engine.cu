@@ -113,6 +113,14 @@ struct emvs_context {
   unsigned int* d_work = nullptr;
   uint32_t vote_ctas_per_sm = 7;       // EMVS_VOTE_CTAS_PER_SM: resident CTAs per SM of the persistent vote grid (1..8)
   int vote_split = -1;                 // EMVS_VOTE_SPLIT: log2 of work items per packet (0..2); -1: automatic
+  // EMVS_VOTE_MULTISLAB: ONE vote launch per build walks all Z-slabs (one scratch buffer per slab, merges started from
+  // per-slab completion counters) instead of one launch per slab; used when the slab buffers fit multislab_budget
+  // (EMVS_MULTISLAB_BUDGET_MB, default 4096: 640x480x256 takes 1.26 GB).  Measured 7.52 against 7.83 ms per stereo
+  // window with device-resident inputs, 9.13 against 10.02 ms through the host-buffer calls (profiles/r2_ab_knobs.md)
+  bool vote_multislab = true;
+  size_t multislab_budget = (size_t)4 << 30;
+  float4* quad_ms = nullptr;  size_t quad_ms_bytes = 0;
+  cudaEvent_t ev_ms_start = nullptr;
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
   // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
   int zero_ctas = 592;                 // EMVS_ZERO_CTAS: grid of the re-zero kernel (its stores carry the evict_last hint); 0: cudaMemsetAsync
@@ -448,8 +456,28 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
   if (use_tma) {
     REQUIRE(n_slabs <= kMaxWorkCounters, EMVS_ERR_INVALID, "build: too many slabs (raise the slab size)");
     REQUIRE(n_packets < (1ull << 31), EMVS_ERR_INVALID, "build: too many packets for one build");
-    if (!ctx->d_work) CUDA_TRY(cudaMalloc((void**)&ctx->d_work, sizeof(unsigned int) * kMaxWorkCounters));
+    // [0, K): work counters (one per vote launch), [K, 2K): per-slab completion counters of a multi-slab launch, [2K]: error word
+    if (!ctx->d_work) {
+      CUDA_TRY(cudaMalloc((void**)&ctx->d_work, sizeof(unsigned int) * (2 * kMaxWorkCounters + 16)));
+      CUDA_TRY(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int) * (2 * kMaxWorkCounters + 16), st));
+    }
     CUDA_TRY(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int) * n_slabs, st));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_work + kMaxWorkCounters, 0, sizeof(unsigned int) * n_slabs, st));
+  }
+  // one vote launch for all slabs of this build?
+  bool multislab = use_tma && ctx->vote_multislab && overlap && n_slabs > 1 && G > 1 && slab % G == 0 &&
+                   (size_t)n_slabs * slab_bytes <= ctx->multislab_budget;
+  if (multislab && (size_t)n_slabs * slab_bytes > ctx->quad_ms_bytes) {
+    if (ctx->quad_ms) CUDA_TRY(cudaFree(ctx->quad_ms));
+    ctx->quad_ms = nullptr;
+    ctx->quad_ms_bytes = 0;
+    if (cudaMalloc((void**)&ctx->quad_ms, (size_t)n_slabs * slab_bytes) != cudaSuccess) {
+      (void)cudaGetLastError();
+      multislab = false;          // not enough memory for one buffer per slab: per-slab launches
+    } else {
+      ctx->quad_ms_bytes = (size_t)n_slabs * slab_bytes;
+      CUDA_TRY(cudaMemsetAsync(ctx->quad_ms, 0, ctx->quad_ms_bytes, st));
+    }
   }
 
   {
@@ -474,17 +502,88 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
   P.ymax = (float)((int)dimY - 1);
   P.QW = QW; P.QH = QH;
 
+  // persistent vote grid (k_vote_tma): vote_ctas_per_sm CTAs per SM take work items from a device-side counter; their
+  // event tiles arrive by cp.async.bulk (TMA) into two shared-memory stages.
+  // 7 of the 8 CTA slots per SM: the eighth (and, at 32 registers per thread, an eighth of the register file) stays
+  // free for the merge / re-zero / peer-reduce kernels that run beside the votes.  Measured (profiles/r2_ab_knobs.md):
+  // 6 per SM is 2 % faster with device-resident inputs but 5 % slower through the host-buffer calls, 8 is the reverse
+  const size_t resident = (size_t)ctx->sm_count * ctx->vote_ctas_per_sm;
+  // work items per packet: whole packets when every resident CTA gets several of them, halves / quarters when a
+  // build is short (head of a split upload, a small shard) so that the dynamic queue can still balance the SMs
+  uint32_t sub = 0;
+  if (ctx->vote_split >= 0) sub = (uint32_t)ctx->vote_split;
+  else while (sub < 2 && (n_packets << sub) < 8 * resident) ++sub;
+  while (sub > 0 && (EMVS_PACKET_SIZE >> sub) / (kVoteThreads / std::max<uint32_t>(G, 1)) < 8) --sub;   // keep the unrolled event loop whole
+  const size_t n_items = n_packets << sub;
+  unsigned int* const d_done = ctx->d_work ? ctx->d_work + kMaxWorkCounters : nullptr;
+  unsigned int* const d_ms_error = ctx->d_work ? ctx->d_work + 2 * kMaxWorkCounters : nullptr;
+#define LAUNCH_VOTE_T(GG, GRID, SMEM, K0, SLAB_PLANES, N_SLABS, DIMZ, QUAD, STRIDE, WC, DONE)                                \
+  do {                                                                                                                      \
+    if (ctx->hint_red == 2)                                                                                                 \
+      k_vote_tma<GG, 2><<<GRID, kVoteThreads, SMEM, st>>>(ctx->d_xy0, d_pk, m->d_depths, K0, SLAB_PLANES, N_SLABS, DIMZ,     \
+                                                          (uint32_t)n_items, sub, P, QUAD, STRIDE, m->d_counts, WC, DONE,  \
+                                                          ctx->hint_xy0);                                                   \
+    else                                                                                                                    \
+      k_vote_tma<GG, 0><<<GRID, kVoteThreads, SMEM, st>>>(ctx->d_xy0, d_pk, m->d_depths, K0, SLAB_PLANES, N_SLABS, DIMZ,     \
+                                                          (uint32_t)n_items, sub, P, QUAD, STRIDE, m->d_counts, WC, DONE,  \
+                                                          ctx->hint_xy0);                                                   \
+  } while (0)
+#define LAUNCH_VOTE_T_ANY(...)                        \
+  switch (G) {                                        \
+    case 2: LAUNCH_VOTE_T(2, __VA_ARGS__); break;     \
+    case 4: LAUNCH_VOTE_T(4, __VA_ARGS__); break;     \
+    case 8: LAUNCH_VOTE_T(8, __VA_ARGS__); break;     \
+    case 16: LAUNCH_VOTE_T(16, __VA_ARGS__); break;   \
+    default: LAUNCH_VOTE_T(32, __VA_ARGS__); break;   \
+  }
+  auto profile_begin = [&](cudaEvent_t* pe1) -> int {
+    *pe1 = nullptr;
+    if (!ctx->profile) return EMVS_OK;
+    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+      cudaEvent_t a, b;
+      CUDA_TRY(cudaEventCreate(&a));
+      CUDA_TRY(cudaEventCreate(&b));
+      ctx->prof_events.push_back(a);
+      ctx->prof_events.push_back(b);
+    }
+    cudaEvent_t pe0 = ctx->prof_events[ctx->prof_used];
+    *pe1 = ctx->prof_events[ctx->prof_used + 1];
+    ctx->prof_used += 2;
+    CUDA_TRY(cudaEventRecord(pe0, st));
+    return EMVS_OK;
+  };
+  const size_t slab_f4 = slab_bytes / sizeof(float4);
+  if (multislab) {
+    // ONE launch votes every slab of this build, slab s into its own scratch buffer; the merges below are queued behind
+    // k_wait_count on the slab's completion counter.  The previous build's merges (which re-zero the same buffers) are
+    // already ordered before this point on `st` (end-of-build wait below).
+    CUDA_TRY(cudaEventRecord(ctx->ev_ms_start, st));              // the counters are zero from here on
+    CUDA_TRY(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_ms_start, 0));
+    cudaEvent_t pe1 = nullptr;
+    { const int rc = profile_begin(&pe1); if (rc) return rc; }
+    const unsigned grid = (unsigned)std::min<size_t>(n_items, resident);
+    LAUNCH_VOTE_T_ANY(grid, vote_tma_smem_bytes(slab), 0u, slab, n_slabs, dimZ, ctx->quad_ms, slab_f4, ctx->d_work, d_done);
+    ctx->launches++;
+    if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
+  }
+
   for (uint32_t k0 = 0; k0 < dimZ; k0 += slab) {
     const uint32_t nk = std::min(slab, dimZ - k0);
     const size_t smem = nk * (sizeof(float4) + sizeof(unsigned int));
-    const int b = overlap ? (int)((k0 / slab) & 1u) : 0;
+    const int b = (overlap && !multislab) ? (int)((k0 / slab) & 1u) : 0;
     cudaStream_t ms = overlap ? ctx->aux_stream : st;   // merge + re-zero stream
-    if (overlap && ctx->merge_pending[b]) {             // buffer b must be merged and zero again (slab s-2)
+    float4* const qbuf = multislab ? ctx->quad_ms + (size_t)(k0 / slab) * slab_f4 : ctx->quad[b];
+    if (multislab) {
+      // the merge of this slab may start when its last vote has landed: n_items items counted by the vote CTAs
+      k_wait_count<<<1, 32, 0, ms>>>(d_done + k0 / slab, (unsigned int)n_items, 20000000000LL, d_ms_error);
+      ctx->launches++;
+    }
+    if (!multislab && overlap && ctx->merge_pending[b]) {             // buffer b must be merged and zero again (slab s-2)
       CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_merge[b], 0));
       ctx->merge_pending[b] = false;
     }
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (ctx->profile) {
+    if (ctx->profile && !multislab) {
       if (ctx->prof_used + 2 > ctx->prof_events.size()) {
         cudaEvent_t a, b;
         CUDA_TRY(cudaEventCreate(&a));
@@ -499,40 +598,12 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     }
     const size_t smem_g = smem + (EMVS_PACKET_SIZE + nk) * sizeof(float2);   // + the packet's warped events + prepared reciprocals
     static const bool fastdiv = [] { const char* e = getenv("EMVS_VOTE_FASTDIV"); return e ? atoi(e) != 0 : false; }();
-    if (use_tma) {
-      // persistent grid: vote_ctas_per_sm CTAs per SM take packets from the slab's work counter; their event tiles
-      // arrive by cp.async.bulk (TMA) into two shared-memory stages
-      // 7 of the 8 CTA slots per SM: the eighth (and, at 32 registers per thread, an eighth of the register file) stays
-      // free for the merge / re-zero / peer-reduce kernels that run beside the votes.  Measured (profiles/r2_ab_knobs.md):
-      // 6 per SM is 2 % faster with device-resident inputs but 5 % slower through the host-buffer calls, 8 is the reverse
-      const size_t resident = (size_t)ctx->sm_count * ctx->vote_ctas_per_sm;
-      // work items per packet: whole packets when every resident CTA gets several of them, halves / quarters when a
-      // build is short (head of a split upload, a small shard) so that the dynamic queue can still balance the SMs
-      uint32_t sub = 0;
-      if (ctx->vote_split >= 0) sub = (uint32_t)ctx->vote_split;
-      else while (sub < 2 && (n_packets << sub) < 8 * resident) ++sub;
-      while (sub > 0 && (EMVS_PACKET_SIZE >> sub) / (kVoteThreads / G) < 8) --sub;   // keep the unrolled event loop whole
-      const size_t n_items = n_packets << sub;
+    if (multislab) {
+      // voted by the build's single launch above
+    } else if (use_tma) {
       const unsigned grid = (unsigned)std::min<size_t>(n_items, resident);
-      const size_t smem_t = vote_tma_smem_bytes(nk);
-      unsigned int* wc = ctx->d_work + k0 / slab;
-#define LAUNCH_VOTE_T(GG)                                                                                                 \
-  do {                                                                                                                    \
-    if (ctx->hint_red == 2)                                                                                               \
-      k_vote_tma<GG, 2><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_items, sub, P, \
-                                                            ctx->quad[b], m->d_counts, wc, ctx->hint_xy0);                \
-    else                                                                                                                  \
-      k_vote_tma<GG, 0><<<grid, kVoteThreads, smem_t, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, (uint32_t)n_items, sub, P, \
-                                                            ctx->quad[b], m->d_counts, wc, ctx->hint_xy0);                \
-  } while (0)
-      switch (G) {
-        case 2: LAUNCH_VOTE_T(2); break;
-        case 4: LAUNCH_VOTE_T(4); break;
-        case 8: LAUNCH_VOTE_T(8); break;
-        case 16: LAUNCH_VOTE_T(16); break;
-        default: LAUNCH_VOTE_T(32); break;
-      }
-#undef LAUNCH_VOTE_T
+      LAUNCH_VOTE_T_ANY(grid, vote_tma_smem_bytes(nk), k0, nk, 1u, k0 + nk, ctx->quad[b], (size_t)0, ctx->d_work + k0 / slab,
+                        (unsigned int*)nullptr);
     } else {
 #define LAUNCH_VOTE_GF(GG, FF)                                                                                         \
   k_vote_grouped<GG, FF><<<(unsigned)n_packets, kVoteThreads, smem_g, st>>>(ctx->d_xy0, d_pk, m->d_depths, k0, nk, P, ctx->quad[b], \
@@ -554,9 +625,9 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
 #undef LAUNCH_VOTE_G
 #undef LAUNCH_VOTE_GF
     }
-    ctx->launches++;
+    if (!multislab) ctx->launches++;
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
-    if (overlap) {
+    if (overlap && !multislab) {
       CUDA_TRY(cudaEventRecord(ctx->ev_vote[b], st));
       CUDA_TRY(cudaStreamWaitEvent(ms, ctx->ev_vote[b], 0));
     }
@@ -568,7 +639,7 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
       const dim3 mg(ceil_div(QW, 256 / G), QH, ceil_div(nk, G));
       float* dst = g->d + (size_t)k0 * dimX * dimY;
 #define LAUNCH_MERGE_G(GG) \
-  k_merge_quads_grouped<GG><<<mg, 256, 0, ms>>>(ctx->quad[b], dst, dimX, dimY, QW, QH, nk, accumulate ? 1 : 0, ctx->hint_dsi)
+  k_merge_quads_grouped<GG><<<mg, 256, 0, ms>>>(qbuf, dst, dimX, dimY, QW, QH, nk, accumulate ? 1 : 0, ctx->hint_dsi)
       switch (G) {
         case 2: LAUNCH_MERGE_G(2); break;
         case 4: LAUNCH_MERGE_G(4); break;
@@ -579,7 +650,7 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
 #undef LAUNCH_MERGE_G
     } else {
       dim3 mb(32, 8, 1), mg(ceil_div(QW, 32), ceil_div(QH, 8), nk);
-      k_merge_quads<<<mg, mb, 0, ms>>>(ctx->quad[b], g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
+      k_merge_quads<<<mg, mb, 0, ms>>>(qbuf, g->d + (size_t)k0 * dimX * dimY, dimX, dimY, QW, QH,
                                        accumulate ? 1 : 0, (int)G);
     }
     ctx->launches++;
@@ -590,10 +661,10 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
       const size_t n_f4 = (size_t)round_up_g(nk) * QW * QH * 4;
       if (dbg_skip_zero) {
       } else if (zero_ctas > 0) {
-        k_zero_f4<<<(unsigned)zero_ctas, 256, 0, ms>>>(ctx->quad[b], n_f4, ctx->hint_zero);
+        k_zero_f4<<<(unsigned)zero_ctas, 256, 0, ms>>>(qbuf, n_f4, ctx->hint_zero);
         ctx->launches++;
       } else {
-        CUDA_TRY(cudaMemsetAsync(ctx->quad[b], 0, n_f4 * sizeof(float4), ms));
+        CUDA_TRY(cudaMemsetAsync(qbuf, 0, n_f4 * sizeof(float4), ms));
       }
     }
     if (overlap) {
@@ -621,6 +692,8 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
         return EMVS_ERR_NCCL;
     }
   }
+#undef LAUNCH_VOTE_T_ANY
+#undef LAUNCH_VOTE_T
   // everything later on `stream` (fusion, download, the next build) sees the finished DSI
   for (int b = 0; b < 2; ++b)
     if (ctx->merge_pending[b]) {
@@ -789,6 +862,9 @@ int emvs_context_create(int device, emvs_context** out)
   if (const char* env = getenv("EMVS_VOTE_KERNEL")) ctx->vote_tma = strcmp(env, "classic") != 0;
   if (const char* env = getenv("EMVS_VOTE_CTAS_PER_SM")) ctx->vote_ctas_per_sm = (uint32_t)std::min(8, std::max(1, atoi(env)));
   ctx->vote_split = std::min(2, std::max(-1, env_int("EMVS_VOTE_SPLIT", ctx->vote_split)));
+  ctx->vote_multislab = env_int("EMVS_VOTE_MULTISLAB", ctx->vote_multislab ? 1 : 0) != 0;
+  ctx->multislab_budget = (size_t)std::max(0, env_int("EMVS_MULTISLAB_BUDGET_MB", (int)(ctx->multislab_budget >> 20))) << 20;
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ms_start, cudaEventDisableTiming);
   ctx->zero_ctas = std::max(0, env_int("EMVS_ZERO_CTAS", ctx->zero_ctas));
   ctx->peer_reduce_ctas = std::max(0, env_int("EMVS_PEER_REDUCE_CTAS", ctx->peer_reduce_ctas));
   ctx->fc_v4 = env_int("EMVS_FC_V4", ctx->fc_v4 ? 1 : 0) != 0;
@@ -854,6 +930,8 @@ static void context_release(emvs_context* ctx)
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaFree(ctx->d_xy0);
   cudaFree(ctx->d_work);
+  cudaFree(ctx->quad_ms);
+  if (ctx->ev_ms_start) cudaEventDestroy(ctx->ev_ms_start);
   cudaFree(ctx->d_out);
   cudaFree(ctx->d_fc_part);
   cudaFree(ctx->d_partial);

@@ -61,7 +61,8 @@ def test_soa_equals_aos_and_oracle(ctx, small_case):
         m.close()
 
 
-@pytest.mark.parametrize("env", [{"EMVS_VOTE_KERNEL": "classic"}, {"EMVS_VOTE_CTAS_PER_SM": "1"}, {"EMVS_VOTE_CTAS_PER_SM": "8"},
+@pytest.mark.parametrize("env", [{"EMVS_VOTE_MULTISLAB": "1"}, {"EMVS_VOTE_MULTISLAB": "0"}, {"EMVS_SLAB": "24"}, {"EMVS_MULTISLAB_BUDGET_MB": "1"},
+                                 {"EMVS_VOTE_KERNEL": "classic"}, {"EMVS_VOTE_CTAS_PER_SM": "1"}, {"EMVS_VOTE_CTAS_PER_SM": "8"},
                                  {"EMVS_ZERO_CTAS": "0", "EMVS_HINT_RED": "0", "EMVS_HINT_XY0": "0", "EMVS_HINT_DSI": "0"},
                                  {"EMVS_HINT_XY0": "2", "EMVS_HINT_ZERO": "1"}, {"EMVS_VOTE_GROUP": "4"}, {"EMVS_VOTE_GROUP": "16"},
                                  {"EMVS_VOTE_SPLIT": "0"}, {"EMVS_VOTE_SPLIT": "2"}, {"EMVS_FC_V4": "0", "EMVS_FC_ZSPLIT": "4"}],
