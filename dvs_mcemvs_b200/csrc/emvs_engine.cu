@@ -120,6 +120,7 @@ struct emvs_context {
   bool vote_multislab = true;
   size_t multislab_budget = (size_t)4 << 30;
   float4* quad_ms = nullptr;  size_t quad_ms_bytes = 0;
+  bool ms_check_pending = false;       // a multi-slab build was issued since the error word was last read (emvs_context_sync)
   cudaEvent_t ev_ms_start = nullptr;
   bool vote_tma = true;                // EMVS_VOTE_KERNEL=classic selects k_vote_grouped (one CTA per packet, A/B baseline)
   // tuning / experiment knobs, read from the environment when the context is created (tools/ab_bench.py)
@@ -564,6 +565,7 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     const unsigned grid = (unsigned)std::min<size_t>(n_items, resident);
     LAUNCH_VOTE_T_ANY(grid, vote_tma_smem_bytes(slab), 0u, slab, n_slabs, dimZ, ctx->quad_ms, slab_f4, ctx->d_work, d_done);
     ctx->launches++;
+    ctx->ms_check_pending = true;
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
   }
 
@@ -950,6 +952,17 @@ int emvs_context_sync(emvs_context* ctx)
   REQUIRE(ctx, EMVS_ERR_INVALID, "context is NULL");
   DeviceGuard guard(ctx->device);
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ms_check_pending && ctx->d_work) {
+    // k_wait_count gives up after ~10 s instead of hanging the device; a merge that ran on an unfinished slab is an error
+    ctx->ms_check_pending = false;
+    unsigned int err = 0;
+    CUDA_TRY(cudaMemcpy(&err, ctx->d_work + 2 * kMaxWorkCounters, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) {
+      CUDA_TRY(cudaMemset(ctx->d_work + 2 * kMaxWorkCounters, 0, sizeof(err)));
+      set_error("a slab's vote completion counter timed out: the DSIs built since the last emvs_context_sync are incomplete");
+      return EMVS_ERR_CUDA;
+    }
+  }
   return EMVS_OK;
 }
 
