@@ -580,12 +580,13 @@ class MapperEMVS:
         # the engine recognises the later call by the arrays' addresses: keep them (and the poses) alive until then
         self.ctx._prefetch_ref = (events, trajectory)
 
-    def evaluateDSI(self, events, trajectory, T_rv_w, allreduce=False, peer_reduce=False):
+    def evaluateDSI(self, events, trajectory, T_rv_w, allreduce=False, peer_reduce=False, accumulate=False):
         """bool evaluateDSI(events, trajectory, T_rv_w) — mapper_emvs_stereo.cpp:67-148.
         `events`: EVENT_DTYPE array (std::vector<dvs_msgs::Event>) or EventsSoA.
-        allreduce / peer_reduce: the events are this rank's shard of a multi-GPU build."""
+        allreduce / peer_reduce: the events are this rank's shard of a multi-GPU build; accumulate: vote on top of the
+        current DSI instead of resetting it (EMVS_BUILD_ACCUMULATE, sub-interval style)."""
         T = ptr(np.ascontiguousarray(T_rv_w, dtype=POSE_DTYPE))
-        flags = self._flags(False, allreduce, peer_reduce)
+        flags = self._flags(accumulate, allreduce, peer_reduce)
         if isinstance(events, EventsSoA):
             es = events.c_struct()
             rc = _lib().emvs_mapper_evaluate_dsi_soa(self._h, C.byref(es), ptr(trajectory.poses), trajectory.poses.shape[0], T, flags)

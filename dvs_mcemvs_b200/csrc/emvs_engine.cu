@@ -143,7 +143,17 @@ struct emvs_context {
   // evaluate_dsi on an idle pipeline: the head of the event list (split_percent %) is uploaded and voted first
   // while the tail is still crossing PCIe (see emvs_mapper_evaluate_dsi_flags); 0 disables
   uint32_t split_percent = 15;
-  int split_pieces = 2;                // EMVS_UPLOAD_PIECES: 2 = head + tail (default), 3 = p % / 3p % / rest (measured slower: every extra piece is 16 short vote launches)
+  int split_pieces = 2;                // EMVS_UPLOAD_PIECES (2..4): pieces of p %, 2.2 p %, 2.2^2 p % ... of the list, the last one takes the rest
+  // EMVS_UPLOAD_DEFER_MERGE: the pieces of a split upload before the last one only VOTE (into the per-slab scratch of the
+  // multi-slab launch, which persists between launches); the last piece votes on top and merges once.  Without it every
+  // piece is a complete build (merge + re-zero of all slabs, accumulating from the second piece on).
+  // Used for builds that take the multi-slab launch and are not part of a peer exchange, with its own geometry
+  // (defer_percent / defer_pieces); every other build splits into split_pieces complete builds.  Measured: stock e2e 8.69
+  // against 9.15 ms per stereo window (profiles/r2_e2e.md, trip 23).
+  bool split_defer_merge = true;
+  uint32_t defer_percent = 6;          // EMVS_UPLOAD_DEFER_SPLIT
+  int defer_pieces = 4;                // EMVS_UPLOAD_DEFER_PIECES (2..4)
+  bool deferred_votes = false;         // the scratch of quad_ms holds votes of a piece whose merge is still to come
   size_t split_min_events = (size_t)1 << 20;
   // NCCL
   void* comm = nullptr;
@@ -364,6 +374,10 @@ struct EventSrc {
 };
 
 constexpr uint32_t kMaxWorkCounters = 4096;    // vote launches (slabs) per build
+// internal build flags of the split upload (never part of the C-ABI's EMVS_BUILD_* values)
+constexpr int kPublicBuildFlags = EMVS_BUILD_ACCUMULATE | EMVS_BUILD_ALLREDUCE | EMVS_BUILD_PEER_REDUCE;
+constexpr int kBuildDeferMerge = 1 << 16;      // vote only: the votes stay in the multi-slab scratch
+constexpr int kBuildContinue = 1 << 17;        // the scratch holds votes of earlier pieces: vote on top, merge everything
 
 // gentle re-zeroing of a merged scratch buffer: 256-thread CTAs that fit beside the persistent vote grid
 __global__ void __launch_bounds__(256) k_zero_f4(float4* __restrict__ p, size_t n, int hint)
@@ -379,6 +393,17 @@ __global__ void __launch_bounds__(256) k_zero_f4(float4* __restrict__ p, size_t 
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = z;
 }
 
+// Would a build into a DSI of this size take the single multi-slab vote launch (one scratch buffer per slab)?
+static bool multislab_eligible(const emvs_context* ctx, uint32_t dimX, uint32_t dimY, uint32_t dimZ)
+{
+  const SlabPlan plan = choose_slab(ctx, dimX, dimY, dimZ);
+  const uint32_t G = plan.group, slab = plan.slab;
+  if (!(ctx->vote_tma && ctx->vote_multislab && ctx->overlap && G > 1 && slab % G == 0)) return false;
+  const uint32_t n_slabs = (dimZ + slab - 1) / slab;
+  const size_t slab_bytes = (size_t)((slab + G - 1) / G * G) * ceil_div(dimX, 2) * ceil_div(dimY, 2) * 4 * sizeof(float4);
+  return n_slabs > 1 && (size_t)n_slabs * slab_bytes <= ctx->multislab_budget;
+}
+
 // Device part of evaluateDSI: event stage, (reset), slab loop of {vote, merge, re-zero[, allreduce | peer reduce]}.
 int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const emvs_packet* d_pk,
                     size_t n_packets, int flags)
@@ -387,6 +412,9 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
   emvs_grid* g = m->grid;
   const bool accumulate = (flags & EMVS_BUILD_ACCUMULATE) != 0;
   const bool reduce = (flags & EMVS_BUILD_ALLREDUCE) != 0;
+  // internal (split upload): vote only, leave the votes in the per-slab scratch / vote on top of such votes and merge
+  const bool want_defer = (flags & kBuildDeferMerge) != 0;
+  const bool cont = (flags & kBuildContinue) != 0;
   cudaStream_t st = ctx->stream;
   const bool peer = (flags & EMVS_BUILD_PEER_REDUCE) != 0;
   emvs_exchange* ex = peer ? ctx->active_exchange : nullptr;
@@ -408,10 +436,10 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     nccl = nccl_api();
     if (!nccl) return EMVS_ERR_NCCL;
   }
-  if (!accumulate) {
+  if (!accumulate && !cont) {
     CUDA_TRY(cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned long long) * g->dimZ, st));
   }
-  if (n_packets == 0) {
+  if (n_packets == 0 && !cont) {
     if (!accumulate) CUDA_TRY(cudaMemsetAsync(g->d, 0, g->n_cells * sizeof(float), st));
     if (reduce) {  // this rank has no packets but must issue the SAME sequence of collectives as the others
       const uint32_t zslab = choose_slab(ctx, g->dimX, g->dimY, g->dimZ).slab;
@@ -466,8 +494,14 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     CUDA_TRY(cudaMemsetAsync(ctx->d_work + kMaxWorkCounters, 0, sizeof(unsigned int) * n_slabs, st));
   }
   // one vote launch for all slabs of this build?
-  bool multislab = use_tma && ctx->vote_multislab && overlap && n_slabs > 1 && G > 1 && slab % G == 0 &&
-                   (size_t)n_slabs * slab_bytes <= ctx->multislab_budget;
+  bool multislab = multislab_eligible(ctx, dimX, dimY, dimZ);
+  REQUIRE(!cont || (multislab && ctx->deferred_votes && (size_t)n_slabs * slab_bytes <= ctx->quad_ms_bytes), EMVS_ERR_STATE,
+          "build: no deferred votes to continue from");
+  if (multislab && !cont && ctx->deferred_votes) {
+    // a split upload was abandoned between its pieces (an error return): its votes must not leak into this build
+    CUDA_TRY(cudaMemsetAsync(ctx->quad_ms, 0, ctx->quad_ms_bytes, st));
+    ctx->deferred_votes = false;
+  }
   if (multislab && (size_t)n_slabs * slab_bytes > ctx->quad_ms_bytes) {
     if (ctx->quad_ms) CUDA_TRY(cudaFree(ctx->quad_ms));
     ctx->quad_ms = nullptr;
@@ -480,8 +514,11 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
       CUDA_TRY(cudaMemsetAsync(ctx->quad_ms, 0, ctx->quad_ms_bytes, st));
     }
   }
+  // vote-only piece of a split upload: possible when this build takes the single multi-slab launch (else it is a plain build
+  // and the caller continues with EMVS_BUILD_ACCUMULATE: ctx->deferred_votes stays false)
+  const bool defer = want_defer && multislab;
 
-  {
+  if (n_packets) {
     const unsigned blocks = (unsigned)((n_voted + 255) / 256);
     if (d_ev.aos)
       k_warp_events<<<blocks, 256, 0, st>>>(d_ev.aos, d_pk, m->d_lut, m->cam.width, m->cam.height, ctx->d_xy0,
@@ -563,13 +600,18 @@ int build_on_device(emvs_mapper* m, const EventSrc& d_ev, size_t n_events, const
     cudaEvent_t pe1 = nullptr;
     { const int rc = profile_begin(&pe1); if (rc) return rc; }
     const unsigned grid = (unsigned)std::min<size_t>(n_items, resident);
-    LAUNCH_VOTE_T_ANY(grid, vote_tma_smem_bytes(slab), 0u, slab, n_slabs, dimZ, ctx->quad_ms, slab_f4, ctx->d_work, d_done);
-    ctx->launches++;
+    if (n_items) {
+      // a deferred piece publishes nothing: the launch of the piece that merges is ordered after it on the stream
+      LAUNCH_VOTE_T_ANY(grid, vote_tma_smem_bytes(slab), 0u, slab, n_slabs, dimZ, ctx->quad_ms, slab_f4, ctx->d_work,
+                        defer ? (unsigned int*)nullptr : d_done);
+      ctx->launches++;
+    }
     ctx->ms_check_pending = true;
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, st));
+    ctx->deferred_votes = defer;
   }
 
-  for (uint32_t k0 = 0; k0 < dimZ; k0 += slab) {
+  for (uint32_t k0 = 0; k0 < dimZ && !defer; k0 += slab) {
     const uint32_t nk = std::min(slab, dimZ - k0);
     const size_t smem = nk * (sizeof(float4) + sizeof(unsigned int));
     const int b = (overlap && !multislab) ? (int)((k0 / slab) & 1u) : 0;
@@ -878,7 +920,10 @@ int emvs_context_create(int device, emvs_context** out)
   ctx->hint_dsi = env_int("EMVS_HINT_DSI", ctx->hint_dsi) != 0 ? 1 : 0;
   ctx->hint_zero = std::min(2, std::max(0, env_int("EMVS_HINT_ZERO", ctx->hint_zero)));
   if (const char* env = getenv("EMVS_UPLOAD_SPLIT")) ctx->split_percent = (uint32_t)std::min(90, std::max(0, atoi(env)));
-  ctx->split_pieces = std::min(3, std::max(2, env_int("EMVS_UPLOAD_PIECES", ctx->split_pieces)));
+  ctx->split_pieces = std::min(4, std::max(2, env_int("EMVS_UPLOAD_PIECES", ctx->split_pieces)));
+  ctx->split_defer_merge = env_int("EMVS_UPLOAD_DEFER_MERGE", ctx->split_defer_merge ? 1 : 0) != 0;
+  ctx->defer_percent = (uint32_t)std::min(60, std::max(1, env_int("EMVS_UPLOAD_DEFER_SPLIT", (int)ctx->defer_percent)));
+  ctx->defer_pieces = std::min(4, std::max(2, env_int("EMVS_UPLOAD_DEFER_PIECES", ctx->defer_pieces)));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ctx->ev_pk_free[b], cudaEventDisableTiming);
@@ -1900,23 +1945,37 @@ static int evaluate_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_st
   const bool exchange = (flags & EMVS_BUILD_ALLREDUCE) != 0;
   const int head_flags = flags & ~EMVS_BUILD_PEER_REDUCE;
   size_t n_head = 0;
+  // vote-only early pieces (see split_defer_merge) where the build takes the multi-slab launch; not under a peer exchange
+  // (that combination has not been run on hardware: such builds keep the head + tail form)
+  const bool defer_mode = ctx->split_defer_merge && !(flags & EMVS_BUILD_PEER_REDUCE) &&
+                          multislab_eligible(ctx, m->grid->dimX, m->grid->dimY, m->grid->dimZ);
+  const uint32_t split_percent = defer_mode ? ctx->defer_percent : ctx->split_percent;
+  const int split_pieces = defer_mode ? ctx->defer_pieces : ctx->split_pieces;
   if (ctx->split_percent && !exchange && n_events >= ctx->split_min_events && n_events >= 4 * (size_t)EMVS_PACKET_SIZE) {
     const cudaError_t q = cudaStreamQuery(ctx->stream);
-    if (q == cudaSuccess) n_head = (n_events / 100 * ctx->split_percent) / EMVS_PACKET_SIZE * EMVS_PACKET_SIZE;
+    if (q == cudaSuccess) n_head = (n_events / 100 * split_percent) / EMVS_PACKET_SIZE * EMVS_PACKET_SIZE;
     else if (q == cudaErrorNotReady) (void)cudaGetLastError();   // "busy" is an answer, not an error: do not leave it behind
     else CUDA_TRY(q);
   }
   if (n_head >= EMVS_PACKET_SIZE) {
-    // Pieces [0, c0), [c0, c1), ..., [c_last, n).  Default: head + tail.  With split_pieces = 3 and p = split_percent
-    // the cuts are p % and 4p % (10 / 30 / 60 % at p = 10): every piece's upload would hide under the previous piece's
-    // votes — measured SLOWER (10.8 vs 10.1 ms per stock step, profiles/r2_e2e.md): an extra piece is 16 more short vote
-    // launches + accumulating merges, which cost more than the exposed quarter millisecond of upload they hide.
-    size_t cuts[3];
+    // Pieces [0, c0), [c0, c1), ..., [c_last, n).  Default: head + tail.  With split_pieces = 3 or 4 the pieces grow by a
+    // factor 2.2 (p, 2.2 p, 4.84 p % of the list, the last one takes the rest): PCIe delivers events about 2.4 times faster
+    // than they are voted, so every piece's upload hides under the previous piece's votes.  As complete builds extra pieces
+    // were measured SLOWER (10.1 vs 9.1 ms per stock step with 3 pieces, profiles/r2_e2e.md: each is one more merge + re-zero
+    // pass over all slabs); with split_defer_merge the pieces before the last only vote.
+    size_t cuts[5];
     int n_cuts = 0;
     cuts[n_cuts++] = n_head;
-    if (ctx->split_pieces >= 3 && 4 * ctx->split_percent <= 70) {
-      const size_t c1 = (n_events / 100 * (4 * ctx->split_percent)) / EMVS_PACKET_SIZE * EMVS_PACKET_SIZE;
-      if (c1 > n_head + EMVS_PACKET_SIZE && c1 + EMVS_PACKET_SIZE < n_events) cuts[n_cuts++] = c1;
+    {
+      double piece = (double)split_percent, cum = piece;
+      while (n_cuts < split_pieces - 1) {
+        piece *= 2.2;
+        cum += piece;
+        if (cum > 75.0) break;
+        const size_t c = (size_t)((double)n_events * cum / 100.0) / EMVS_PACKET_SIZE * EMVS_PACKET_SIZE;
+        if (c <= cuts[n_cuts - 1] + EMVS_PACKET_SIZE || c + EMVS_PACKET_SIZE >= n_events) break;
+        cuts[n_cuts++] = c;
+      }
     }
     cuts[n_cuts] = n_events;   // sentinel: the end of the list
     rc = upload_events(ctx, ev, 0, cuts[0]);
@@ -1930,10 +1989,12 @@ static int evaluate_dsi_impl(emvs_mapper* m, const HostEvents& ev, const emvs_st
                                                ctx->h_packets + n_pk_done, max_pk - n_pk_done);
       const size_t next_lo = last ? 0 : cuts[k], next_hi = last ? 0 : cuts[k + 1];
       // only the LAST build into the DSI announces its slabs to the peers; an empty last piece still has to
-      const bool must_build = n_pk > 0 || (last && (!built || (flags & EMVS_BUILD_PEER_REDUCE)));
+      const bool must_build = n_pk > 0 || (last && (!built || ctx->deferred_votes || (flags & EMVS_BUILD_PEER_REDUCE)));
       if (must_build) {
         int f = last ? flags : head_flags;
-        if (built) f |= EMVS_BUILD_ACCUMULATE;
+        // earlier pieces left their votes in the scratch (deferred merge): vote on top; else they are in the DSI: accumulate
+        if (built) f |= ctx->deferred_votes ? kBuildContinue : EMVS_BUILD_ACCUMULATE;
+        if (!last && defer_mode && (!built || ctx->deferred_votes)) f |= kBuildDeferMerge;
         rc = build_from_host(m, ev, ctx->h_packets + n_pk_done, n_pk, f, true, next_lo, next_hi);
         if (rc) return rc;
         built = true;
@@ -2030,6 +2091,7 @@ int emvs_mapper_build(emvs_mapper* m, const emvs_event* events, size_t n_events,
 {
   REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
   REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE((flags & ~kPublicBuildFlags) == 0, EMVS_ERR_INVALID, "mapper_build: unknown build flag");
   REQUIRE(n_packets == 0 || (events && packets), EMVS_ERR_INVALID, "mapper_build: NULL events/packets");
   int rc = check_packets(packets, n_packets, n_events);
   if (rc) return rc;
@@ -2044,6 +2106,7 @@ int emvs_mapper_build_device(emvs_mapper* m, const void* d_events, size_t n_even
 {
   REQUIRE(m, EMVS_ERR_INVALID, "mapper is NULL");
   REQUIRE(m->lut_set, EMVS_ERR_STATE, "mapper_build_device: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE((flags & ~kPublicBuildFlags) == 0, EMVS_ERR_INVALID, "mapper_build_device: unknown build flag");
   REQUIRE(n_packets == 0 || (d_events && d_packets), EMVS_ERR_INVALID, "mapper_build_device: NULL events/packets");
   DeviceGuard guard(m->ctx->device);
   EventSrc src;
@@ -2067,6 +2130,7 @@ int emvs_mapper_evaluate_dsi_flags(emvs_mapper* m, const emvs_event* events, siz
     return EMVS_ERR_TOO_FEW;
   }
   REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE((flags & ~kPublicBuildFlags) == 0, EMVS_ERR_INVALID, "evaluate_dsi: unknown build flag");
   DeviceGuard guard(m->ctx->device);
   return evaluate_dsi_impl(m, host_aos(events, n_events), traj, n_poses, T_rv_w, flags);
 }
@@ -2083,6 +2147,7 @@ int emvs_mapper_evaluate_dsi_soa(emvs_mapper* m, const emvs_events_soa* events, 
     return EMVS_ERR_TOO_FEW;
   }
   REQUIRE(m->lut_set, EMVS_ERR_STATE, "evaluate_dsi_soa: rectification LUT not set (emvs_mapper_set_lut)");
+  REQUIRE((flags & ~kPublicBuildFlags) == 0, EMVS_ERR_INVALID, "evaluate_dsi_soa: unknown build flag");
   DeviceGuard guard(m->ctx->device);
   return evaluate_dsi_impl(m, host_soa(events), traj, n_poses, T_rv_w, flags);
 }

@@ -676,9 +676,20 @@ def test_config5_sweep_corners(ctx, O, dims, n_ev):
     m.close()
 
 
-def test_evaluate_dsi_three_piece_split(small_case):
-    """EMVS_UPLOAD_PIECES=3 (p %, 4p %, rest; off by default): the three builds add up to the one-piece DSI — counts
-    bit-exact.  Read when a context is created, hence a fresh process."""
+@pytest.mark.parametrize("env,percent,pieces,deferred", [
+    ({"EMVS_UPLOAD_PIECES": "3"}, 10, 3, False),                                                  # one slab: never deferred
+    ({"EMVS_UPLOAD_PIECES": "4", "EMVS_UPLOAD_DEFER_MERGE": "0", "EMVS_SLAB": "24"}, 6, 4, False),
+    ({"EMVS_SLAB": "24"}, 15, 4, True),                                                           # the defaults: 4 pieces from 6 %
+    ({"EMVS_UPLOAD_DEFER_PIECES": "2", "EMVS_UPLOAD_DEFER_SPLIT": "15", "EMVS_SLAB": "24"}, 15, 2, True),
+    ({"EMVS_UPLOAD_DEFER_PIECES": "3", "EMVS_UPLOAD_DEFER_SPLIT": "8", "EMVS_SLAB": "24"}, 15, 3, True),
+    ({}, 15, 2, False),                                                                           # one slab, defaults: head + tail
+], ids=["three", "four", "four_deferred", "two_deferred", "three_deferred", "default_single_slab"])
+def test_evaluate_dsi_multi_piece_split(small_case, env, percent, pieces, deferred):
+    """Split upload in more than two pieces (p %, 2.2 p %, 4.84 p %, rest).  As complete builds (EMVS_UPLOAD_PIECES, default 2)
+    and in the deferred form that builds taking the multi-slab vote launch use by default (EMVS_UPLOAD_DEFER_MERGE /
+    _DEFER_PIECES / _DEFER_SPLIT: the pieces before the last one only vote, into the per-slab scratch; the last one votes on
+    top and merges once): the pieces add up to the one-piece DSI — counts bit-exact — and the number of kernel launches
+    says which path ran.  The knobs are read when a context is created, hence a fresh process."""
     import os
     import subprocess
     import sys
@@ -690,19 +701,29 @@ def test_evaluate_dsi_three_piece_split(small_case):
         "from dvs_mcemvs_b200 import api\n"
         "case = Case('esim_small')\n"
         "ctx = api.Context(0)\n"
-        "ctx.set_upload_split(10, 4096)\n"
+        f"ctx.set_upload_split({percent}, 4096)\n"
         "m = api.MapperEMVS(ctx, case.cams[0], case.shape)\n"
-        "n0 = ctx.launch_count()\n"
-        "assert m.evaluateDSI(case.events[0], api.LinearTrajectory(case.trajs[0]), case.T_rv_w)\n"
-        "n3 = ctx.launch_count() - n0\n"
+        "tr = api.LinearTrajectory(case.trajs[0])\n"
         "dsi_o, inb_o = case.oracle_dsi(0)\n"
-        "assert np.array_equal(m.counts(), inb_o)\n"
-        "np.testing.assert_allclose(m.dsi_.download(), dsi_o, rtol=1e-5, atol=1e-5)\n"
+        "for rep in range(2):\n"                                      # twice: the scratch is clean again after a deferred sequence
+        "    ctx.sync(); n0 = ctx.launch_count()\n"
+        "    assert m.evaluateDSI(case.events[0], tr, case.T_rv_w)\n"
+        "    n_split = ctx.launch_count() - n0\n"
+        "    assert np.array_equal(m.counts(), inb_o)\n"
+        "    np.testing.assert_allclose(m.dsi_.download(), dsi_o, rtol=1e-5, atol=1e-5)\n"
         "ctx.set_upload_split(0)\n"
         "ctx.sync(); n0 = ctx.launch_count()\n"
-        "assert m.evaluateDSI(case.events[0], api.LinearTrajectory(case.trajs[0]), case.T_rv_w)\n"
-        "assert n3 == 3 * (ctx.launch_count() - n0)\n"
-        "print('three pieces ok')\n")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, EMVS_UPLOAD_PIECES="3"))
-    assert r.returncode == 0 and "three pieces ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+        "assert m.evaluateDSI(case.events[0], tr, case.T_rv_w)\n"
+        "n_one = ctx.launch_count() - n0\n"
+        "assert np.array_equal(m.counts(), inb_o)\n"
+        f"want = n_one + 2 * ({pieces} - 1) if {deferred} else {pieces} * n_one\n"   # a vote-only piece: event stage + one vote launch
+        "assert n_split == want, (n_split, n_one)\n"
+        # an accumulating evaluate on top of a split one (sub-interval style): counts and volume double
+        f"ctx.set_upload_split({percent}, 4096)\n"
+        "ctx.sync()\n"
+        "assert m.evaluateDSI(case.events[0], tr, case.T_rv_w, accumulate=True)\n"
+        "assert np.array_equal(m.counts(), 2 * inb_o)\n"
+        "np.testing.assert_allclose(m.dsi_.download(), 2 * dsi_o, rtol=1e-5, atol=2e-5)\n"
+        "print('pieces ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+    assert r.returncode == 0 and "pieces ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
