@@ -169,9 +169,13 @@ EMVS_API int emvs_context_sync(emvs_context* ctx);
 EMVS_API int emvs_context_set_slab(emvs_context* ctx, uint32_t planes_per_slab);
 /* Tuning of emvs_mapper_evaluate_dsi on an idle pipeline: the first `percent` % of the event list is uploaded and
  * voted first while the rest is still crossing PCIe, then the rest is voted into the same DSI (votes add);
- * $EMVS_UPLOAD_PIECES=3 cuts the rest once more at 4 x percent % (measured slower).  Lists
+ * $EMVS_UPLOAD_PIECES = 3 / 4 cuts the rest again (pieces grow by 2.2 x; as complete builds measured slower).  Lists
  * shorter than `min_events` are built in one piece; percent = 0 disables.  Defaults: 15 %, 2^20 events
- * ($EMVS_UPLOAD_SPLIT overrides the percentage at context creation). */
+ * ($EMVS_UPLOAD_SPLIT overrides the percentage at context creation).
+ * Builds that take the single multi-slab vote launch and are not part of a peer exchange use the deferred
+ * form instead, with its own geometry ($EMVS_UPLOAD_DEFER_MERGE=1, _DEFER_SPLIT=6, _DEFER_PIECES=4): the pieces before the
+ * last one only vote — their votes stay in the per-slab scratch —, the last one votes on top and merges once.  `percent`
+ * = 0 disables that form too; `min_events` applies to both. */
 EMVS_API int emvs_context_set_upload_split(emvs_context* ctx, uint32_t percent, uint64_t min_events);
 /* Streaming callers (consecutive windows, main.cpp:177-431 full_seq loop): announce the event list of the NEXT
  * emvs_mapper_evaluate_dsi / emvs_mapper_build call on this context.  Its host->device copy starts now, on the copy
