@@ -1,7 +1,8 @@
 // ros_adapters.hpp — conversions from the reference's ROS / minkindr / image_geometry types to the
 // PODs of the host mirror.  Compiled only where those headers exist (a catkin workspace); this
-// image has none of them, so the file is inert here (`__has_include` guards) and is exercised by
-// the maintainer-side build described in INTEGRATION.md §2.
+// image has none of them, so the file is inert here (`__has_include` guards) and is meant for
+// the maintainer-side build described in INTEGRATION.md §2.  tests/test_ros_adapters.py compiles it
+// against shims with the same type and member names (tests/shims/ros/) and runs the conversions.
 #pragma once
 
 #include "mapper_emvs_stereo/mapper_emvs_stereo.hpp"
