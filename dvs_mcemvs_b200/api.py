@@ -175,7 +175,9 @@ class Context:
         check(_lib().emvs_context_set_slab(self._h, int(planes)))
 
     def set_upload_split(self, percent, min_events=1 << 20):
-        """evaluateDSI on an idle pipeline votes the first `percent` % of the events while the rest is uploaded."""
+        """evaluateDSI on an idle pipeline votes the first `percent` % of the events while the rest is uploaded
+        (head + tail as two builds).  Builds on the single multi-slab vote launch use the deferred form with its own
+        geometry instead (emvs_b200.h: EMVS_UPLOAD_DEFER_*); percent = 0 turns both off, min_events applies to both."""
         check(_lib().emvs_context_set_upload_split(self._h, int(percent), int(min_events)))
 
     def prefetch_events(self, events):
